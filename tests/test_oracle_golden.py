@@ -1,0 +1,118 @@
+"""Pin the CPU oracle (oracle/) against the reference: the reference's own compute_perm KAT
+(lib/coarsening.py:261-262) and the fixtures produced by the unmodified reference
+(tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+from oracle import meshnet_oracle as mo
+
+from helpers import CASES, graph_from_fixture, load_npz, rel_err, tensor_digest
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_compute_perm_known_answer():
+    got = go.binary_tree_order([np.array([4, 1, 1, 2, 2, 3, 0, 0, 3]), np.array([2, 1, 0, 1, 0])])
+    assert got == [[3, 4, 0, 9, 1, 2, 5, 8, 6, 7, 10, 11], [2, 4, 1, 3, 0, 5], [0, 1, 2]]
+
+
+def _joint(mano):
+    return (21, go.MANO_SKELETON, go.MANO_HORI_CONN) if mano else (17, go.H36M_SKELETON, go.H36M_FLIP_PAIRS)
+
+
+@pytest.mark.parametrize("name", ["smpl_small", "mano_like", "smpl_like"])
+def test_graph_oracle_matches_reference(name):
+    n, seed, levels, mano = CASES[name]
+    z = load_npz(f"graph_{name}.npz")
+    face = go.synthetic_sphere_faces(n, seed)
+    if "face" in z:
+        assert np.array_equal(face, z["face"])
+    j, sk, fp = _joint(mano)
+    adj, lap, perm, perm_rev = go.build_coarse_graphs(face, j, sk, fp, levels=levels)
+    assert np.array_equal(np.asarray(perm_rev), z["perm_reverse"])
+    assert len(lap) == int(z["n_levels"])
+    for i, m in enumerate(lap):
+        c = m.tocsr()
+        c.sort_indices()
+        assert tuple(c.shape) == tuple(z[f"L{i}_shape"])
+        assert c.nnz == int(z[f"L{i}_nnz"])
+        assert sha(c.indptr.astype(np.int64)) == str(z[f"L{i}_indptr_sha"])
+        assert sha(c.indices.astype(np.int64)) == str(z[f"L{i}_indices_sha"])
+        d32 = c.data.astype(np.float32)
+        ref = z[f"L{i}_data32_sum"]
+        assert abs(d32.astype(np.float64).sum() - ref[0]) <= 1e-6 * max(1.0, abs(ref[0]))
+        assert abs(np.abs(d32).astype(np.float64).sum() - ref[1]) <= 1e-6 * ref[1]
+        if f"L{i}_data" in z:
+            # ARPACK's start vector is not seeded, so lmax may move in the last f64 bits
+            np.testing.assert_allclose(c.data, z[f"L{i}_data"], rtol=1e-12, atol=1e-14)
+
+
+def test_smpl_like_level_sizes_match_real_smpl():
+    z = load_npz("graph_smpl_like.npz")
+    sizes = [int(z[f"L{i}_shape"][0]) for i in range(int(z["n_levels"]))]
+    assert sizes == [12288, 6144, 3072, 1536, 768, 384, 192, 96, 48, 17]   # meshnet.py:27,35-37,117 comments
+    assert int(z["L0_nnz"]) == 6890 + 2 * 20664 + (12288 - 6890)
+
+
+def test_cheb_conv_oracle_matches_reference():
+    z = load_npz("cheb_conv.npz")
+    mats, _ = graph_from_fixture("smpl_small")
+    lap = mo.laplacians_to_torch(mats, drop_second_coarsest=False)[int(z["level"])]
+    x = torch.from_numpy(z["x"])
+    w, b = torch.from_numpy(z["weight"]), torch.from_numpy(z["bias"])
+    y = mo.cheb_conv(x, lap, w, b)
+    assert rel_err(y, torch.from_numpy(z["y_plain"])) < 2e-6
+    fout = w.shape[0]
+    bn = dict(weight=torch.from_numpy(z["bn_weight"]), bias=torch.from_numpy(z["bn_bias"]),
+              running_mean=torch.zeros(fout), running_var=torch.ones(fout))
+    y = mo.cheb_conv(x, lap, w, b, bn, training=True)
+    assert rel_err(y, torch.from_numpy(z["y_bn_train"])) < 2e-6
+    np.testing.assert_allclose(bn["running_mean"].numpy(), z["bn_running_mean"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(bn["running_var"].numpy(), z["bn_running_var"], rtol=1e-5, atol=1e-7)
+    y = mo.cheb_conv(x, lap, w, b, bn, training=False)
+    assert rel_err(y, torch.from_numpy(z["y_bn_eval"])) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
+def test_meshnet_oracle_matches_reference(name):
+    n, seed, levels, mano = CASES[name]
+    z = load_npz(f"meshnet_{name}.npz")
+    mats, _ = graph_from_fixture(name)
+    laps = mo.laplacians_to_torch(mats)
+    sizes = [m.shape[0] for m in laps]
+    torch.manual_seed(123)
+    sd0 = mo.init_state_dict(5, 3, sizes, mano)
+    assert sorted(sd0.keys()) == [str(k) for k in z["keys"]]
+    assert sum(v.numel() for k, v in sd0.items() if "running" not in k and "num_batches" not in k) == int(z["n_param"])
+    for k, v in sd0.items():
+        assert tuple(v.shape) == tuple(z["shape/" + k]), k
+        np.testing.assert_allclose(tensor_digest(v), z["init/" + k], rtol=1e-12, atol=0, err_msg=k)
+
+    x = torch.from_numpy(z["x"])
+    sd_eval = mo.randomize_bn_({k: v.clone() for k, v in sd0.items()}, seed=7)
+    with torch.no_grad():
+        y = mo.forward(sd_eval, laps, x, mano=mano, training=False)
+    assert rel_err(y, torch.from_numpy(z["y_eval"])) < 1e-5
+
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd0.items()}
+    xg = x.clone().requires_grad_(True)
+    y = mo.forward(sd, laps, xg, mano=mano, training=True)
+    assert rel_err(y, torch.from_numpy(z["y_train"])) < 1e-5
+    loss = (y - torch.from_numpy(z["target"])).abs().mean()
+    assert abs(loss.item() - float(z["loss"])) < 1e-5
+    loss.backward()
+    assert rel_err(xg.grad, torch.from_numpy(z["dx"])) < 1e-4
+    for k, v in sd.items():
+        if v.requires_grad:
+            got, ref = tensor_digest(v.grad), z["grad/" + k]
+            assert abs(got[1] - ref[1]) <= 1e-3 * ref[1] + 1e-6, k      # sum |g| (bias grads under BN are pure rounding noise)
+            assert abs(got[2] - ref[2]) <= 2e-3 * ref[2] + 1e-12, k     # sum g^2
+        if "running" in k:
+            np.testing.assert_allclose(v.numpy(), z["after/" + k], rtol=1e-4, atol=1e-6, err_msg=k)
