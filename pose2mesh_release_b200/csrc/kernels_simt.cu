@@ -1,0 +1,616 @@
+// SIMT (CUDA-core, fp32) kernels of the MeshNet hot path: Chebyshev basis SpMM, generic GEMMs with
+// the fused conv epilogue, BatchNorm statistics / apply / backward, basis backward.  These cover
+// every shape (V=17 joint graph, Fin=5, Fout=3 ...) and are the parity baseline and fallback for
+// the tcgen05 path in cheb_umma.cu.  All of it is HBM- or FFMA-bound fp32 work; no tensor cores.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "p2m_internal.h"
+
+namespace p2m {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// =====================================================================================
+// Chebyshev basis  T = [T0 | T1 | T2],  T0 = x, T1 = L~ x, T2 = 2 L~ T1 - x
+// (cheby_graph_conv.py:16-29).  One thread per (row, VEC features); neighbour rows are gathered
+// through L2 — each is a contiguous F*4-byte segment, so a warp reads whole 128-byte lines.
+// =====================================================================================
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> {
+  using type = float4;
+};
+template <>
+struct VecT<1> {
+  using type = float;
+};
+
+__device__ __forceinline__ float4 fma4(float a, float4 x, float4 acc) {
+  acc.x = fmaf(a, x.x, acc.x);
+  acc.y = fmaf(a, x.y, acc.y);
+  acc.z = fmaf(a, x.z, acc.z);
+  acc.w = fmaf(a, x.w, acc.w);
+  return acc;
+}
+__device__ __forceinline__ float fma4(float a, float x, float acc) { return fmaf(a, x, acc); }
+__device__ __forceinline__ float4 zero_of(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float zero_of(float) { return 0.f; }
+// 2*s - x0
+__device__ __forceinline__ float4 two_s_minus(float4 s, float4 x0) {
+  return make_float4(2.f * s.x - x0.x, 2.f * s.y - x0.y, 2.f * s.z - x0.z, 2.f * s.w - x0.w);
+}
+__device__ __forceinline__ float two_s_minus(float s, float x0) { return 2.f * s - x0; }
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_cheb_t01(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                  const float* __restrict__ val, int V, const float* __restrict__ x,
+                                                  int in_unpool, long long rows, int F, float* __restrict__ T) {
+  using vec = typename VecT<VEC>::type;
+  const int fg = F / VEC;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * fg) return;
+  long long r = idx / fg;
+  int f = (int)(idx - r * fg);
+  int v = (int)(r % V);
+  const vec* xv = reinterpret_cast<const vec*>(x);
+  long long pr = in_unpool ? (r >> 1) : r;
+  vec t0 = xv[pr * fg + f];
+  vec acc = zero_of(t0);
+  int p0 = rowptr[v], p1 = rowptr[v + 1];
+  for (int p = p0; p < p1; ++p) {
+    long long rn = r + reloff[p];
+    if (in_unpool) rn >>= 1;
+    acc = fma4(val[p], xv[rn * fg + f], acc);
+  }
+  vec* Tv = reinterpret_cast<vec*>(T);
+  Tv[r * 3 * fg + f] = t0;
+  Tv[r * 3 * fg + fg + f] = acc;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_cheb_t2(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                 const float* __restrict__ val, int V, long long rows, int F,
+                                                 float* __restrict__ T) {
+  using vec = typename VecT<VEC>::type;
+  const int fg = F / VEC;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * fg) return;
+  long long r = idx / fg;
+  int f = (int)(idx - r * fg);
+  int v = (int)(r % V);
+  vec* Tv = reinterpret_cast<vec*>(T);
+  vec t0 = Tv[r * 3 * fg + f];
+  vec acc = zero_of(t0);
+  int p0 = rowptr[v], p1 = rowptr[v + 1];
+  for (int p = p0; p < p1; ++p) {
+    long long rn = r + reloff[p];
+    acc = fma4(val[p], Tv[rn * 3 * fg + fg + f], acc);
+  }
+  Tv[r * 3 * fg + 2 * fg + f] = two_s_minus(acc, t0);
+}
+
+int launch_cheb_basis(const DevLevel& g, const float* x, int in_unpool, int rows, int F, float* T, cudaStream_t s) {
+  if (rows % g.V != 0) {
+    set_error("cheb_basis: rows not a multiple of the level size");
+    return P2M_ERR_INVALID;
+  }
+  const bool v4 = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(T) & 15) == 0);
+  long long n = (long long)rows * (v4 ? F / 4 : F);
+  int grid = cdiv(n, 256);
+  if (v4) {
+    k_cheb_t01<4><<<grid, 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, x, in_unpool, rows, F, T);
+    P2M_LAUNCH_OK();
+    k_cheb_t2<4><<<grid, 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, F, T);
+    P2M_LAUNCH_OK();
+  } else {
+    k_cheb_t01<1><<<grid, 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, x, in_unpool, rows, F, T);
+    P2M_LAUNCH_OK();
+    k_cheb_t2<1><<<grid, 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, F, T);
+    P2M_LAUNCH_OK();
+  }
+  return P2M_OK;
+}
+
+// =====================================================================================
+// Basis backward:  U = dT1 + 2 L~ dT2 ;  dXl = dT0 - dT2 + L~ U (+ resample^T(g_res)),  optional pair-sum
+// =====================================================================================
+template <int VEC>
+__global__ void __launch_bounds__(256) k_basis_bwd_u(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                     const float* __restrict__ val, int V, long long rows, int F,
+                                                     const float* __restrict__ dT, float* __restrict__ U) {
+  using vec = typename VecT<VEC>::type;
+  const int fg = F / VEC;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * fg) return;
+  long long r = idx / fg;
+  int f = (int)(idx - r * fg);
+  int v = (int)(r % V);
+  const vec* Dv = reinterpret_cast<const vec*>(dT);
+  vec acc = zero_of(Dv[0]);
+  int p0 = rowptr[v], p1 = rowptr[v + 1];
+  for (int p = p0; p < p1; ++p) {
+    long long rn = r + reloff[p];
+    acc = fma4(2.f * val[p], Dv[rn * 3 * fg + 2 * fg + f], acc);
+  }
+  vec d1 = Dv[r * 3 * fg + fg + f];
+  reinterpret_cast<vec*>(U)[r * fg + f] = fma4(1.f, d1, acc);
+}
+
+// scalar (per-feature) variant of the final combine: the transposed resampling stencil is per channel.
+__global__ void __launch_bounds__(256) k_basis_bwd_dx(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                      const float* __restrict__ val, int V, long long rows_out, int F,
+                                                      const float* __restrict__ dT, const float* __restrict__ U,
+                                                      const float* __restrict__ g_res, int res_Fout,
+                                                      const int* __restrict__ t_ptr, const int* __restrict__ t_idx,
+                                                      const float* __restrict__ t_w, int pairsum,
+                                                      float* __restrict__ dx) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_out * F) return;
+  long long ro = idx / F;
+  int f = (int)(idx - ro * F);
+  float total = 0.f;
+  const int reps = pairsum ? 2 : 1;
+  for (int q = 0; q < reps; ++q) {
+    long long r = pairsum ? (2 * ro + q) : ro;
+    int v = (int)(r % V);
+    float acc = 0.f;
+    int p0 = rowptr[v], p1 = rowptr[v + 1];
+    for (int p = p0; p < p1; ++p) acc = fmaf(val[p], U[(r + reloff[p]) * F + f], acc);
+    acc += dT[r * 3 * F + f] - dT[r * 3 * F + 2 * F + f];
+    if (g_res != nullptr) {
+      for (int p = t_ptr[f]; p < t_ptr[f + 1]; ++p) acc = fmaf(t_w[p], g_res[r * res_Fout + t_idx[p]], acc);
+    }
+    total += acc;
+  }
+  dx[ro * F + f] = total;
+}
+
+int launch_cheb_basis_bwd(const DevLevel& g, const float* dT, int rows, int F, float* U, const float* g_res,
+                          int res_Fout, const InterpTable* it, int out_pairsum, float* dx, cudaStream_t s) {
+  const bool v4 = (F % 4 == 0);
+  long long n = (long long)rows * (v4 ? F / 4 : F);
+  if (v4) {
+    k_basis_bwd_u<4><<<cdiv(n, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, F, dT, U);
+  } else {
+    k_basis_bwd_u<1><<<cdiv(n, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, F, dT, U);
+  }
+  P2M_LAUNCH_OK();
+  long long rows_out = out_pairsum ? rows / 2 : rows;
+  k_basis_bwd_dx<<<cdiv(rows_out * F, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows_out, F, dT, U, g_res,
+                                                        res_Fout, it ? it->t_ptr : nullptr, it ? it->t_idx : nullptr,
+                                                        it ? it->t_w : nullptr, out_pairsum, dx);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// =====================================================================================
+// Generic fp32 GEMM  C = A * op(B)  with the conv epilogue
+// =====================================================================================
+struct EpiDev {
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int relu;
+  const float* res;
+  int res_F;
+  int res_unpool;
+  const int* i0;
+  const int* i1;
+  const float* lam;
+};
+
+__device__ __forceinline__ float apply_epilogue(float v, long long r, int n, const EpiDev& ep) {
+  if (ep.bias) v += ep.bias[n];
+  if (ep.scale) v = fmaf(v, ep.scale[n], ep.shift[n]);
+  if (ep.relu) v = fmaxf(v, 0.f);
+  if (ep.res) {
+    long long pr = ep.res_unpool ? (r >> 1) : r;
+    const float* rr = ep.res + pr * ep.res_F;
+    float l = ep.lam[n];
+    v += (1.f - l) * rr[ep.i0[n]] + l * rr[ep.i1[n]];
+  }
+  return v;
+}
+
+template <int BM, int BN, int BK, bool B_KN>
+__global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                              float* __restrict__ C, int ldc, int M, int N, int K, EpiDev ep) {
+  constexpr int TM = 8;
+  constexpr int TN = BN / 16;  // 16 thread columns; TN = 8 (BN=128) or 4 (BN=64)
+  static_assert(BM == 128 && (BN == 128 || BN == 64), "tile config");
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int e = tid; e < BM * BK; e += 256) {
+      int row = e / BK, k = e % BK;
+      long long m = m0 + row;
+      As[k][row] = (m < M && k0 + k < K) ? A[m * lda + k0 + k] : 0.f;
+    }
+    if (B_KN) {
+      for (int e = tid; e < BN * BK; e += 256) {
+        int k = e / BN, n = e % BN;
+        Bs[k][n] = (n0 + n < N && k0 + k < K) ? B[(long long)(k0 + k) * ldb + n0 + n] : 0.f;
+      }
+    } else {
+      for (int e = tid; e < BN * BK; e += 256) {
+        int n = e / BK, k = e % BK;
+        Bs[k][n] = (n0 + n < N && k0 + k < K) ? B[(long long)(n0 + n) * ldb + k0 + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+      for (int h = 0; h < TN / 4; ++h) {
+        float4 bv = *reinterpret_cast<const float4*>(&Bs[k][h * 64 + tx * 4]);
+        b[h * 4 + 0] = bv.x; b[h * 4 + 1] = bv.y; b[h * 4 + 2] = bv.z; b[h * 4 + 3] = bv.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int h = 0; h < TN / 4; ++h) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = n0 + h * 64 + tx * 4 + j;
+        if (n < N) C[m * ldc + n] = apply_epilogue(acc[i][h * 4 + j], m, n, ep);
+      }
+    }
+  }
+}
+
+int launch_gemm(const float* A, int lda, const float* B, int ldb, int b_is_kn, float* C, int ldc, int M, int N, int K,
+                const Epilogue& e, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) {
+    set_error("gemm: empty problem");
+    return P2M_ERR_INVALID;
+  }
+  EpiDev ep{e.bias, e.scale, e.shift, e.relu, e.res, e.res_F, e.res_unpool, e.res_i0, e.res_i1, e.res_lam};
+  if (N > 64) {
+    dim3 grid(cdiv(M, 128), cdiv(N, 128));
+    if (b_is_kn)
+      k_gemm<128, 128, 16, true><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
+    else
+      k_gemm<128, 128, 16, false><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
+  } else {
+    dim3 grid(cdiv(M, 128), cdiv(N, 64));
+    if (b_is_kn)
+      k_gemm<128, 64, 16, true><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
+    else
+      k_gemm<128, 64, 16, false><<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
+  }
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// C[N1,N2] += A[M,N1]^T B[M,N2]; each CTA owns a 64x64 output tile and a chunk of M rows.
+constexpr int TN_CHUNK = 2048;
+__global__ void __launch_bounds__(256) k_gemm_tn_atomic(const float* __restrict__ A, int lda,
+                                                        const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                        int ldc, int M, int N1, int N2) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
+  const long long mbeg = (long long)blockIdx.x * TN_CHUNK;
+  const long long mend = min((long long)M, mbeg + TN_CHUNK);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long m0 = mbeg; m0 < mend; m0 += 16) {
+    for (int e = tid; e < 16 * 64; e += 256) {
+      int k = e >> 6, n = e & 63;
+      long long m = m0 + k;
+      As[k][n] = (m < mend && a0 + n < N1) ? A[m * lda + a0 + n] : 0.f;
+      Bs[k][n] = (m < mend && b0 + n < N2) ? B[m * ldb + b0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float a[4] = {av.x, av.y, av.z, av.w};
+      float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = a0 + ty * 4 + i, c = b0 + tx * 4 + j;
+      if (r < N1 && c < N2) atomicAdd(&C[(long long)r * ldc + c], acc[i][j]);
+    }
+}
+
+int launch_gemm_tn_atomic(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N1, int N2,
+                          cudaStream_t s) {
+  dim3 grid(cdiv(M, TN_CHUNK), cdiv(N1, 64), cdiv(N2, 64));
+  k_gemm_tn_atomic<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N1, N2);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// =====================================================================================
+// small helpers
+// =====================================================================================
+__global__ void k_permute_w(const float* __restrict__ W, float* __restrict__ Wp, int fout, int fin, int inverse) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= fout * fin * 3) return;
+  int n = idx / (fin * 3), c = idx % (fin * 3);
+  int f = c / 3, k = c % 3;  // reference column c = f*3 + k  (cheby_graph_conv.py:32-34)
+  int cp = k * fin + f;      // ours: k-major blocks
+  if (!inverse)
+    Wp[n * fin * 3 + cp] = W[idx];
+  else
+    Wp[idx] = W[n * fin * 3 + cp];
+}
+int launch_permute_w(const float* W, float* Wp, int fout, int fin, cudaStream_t s) {
+  k_permute_w<<<cdiv(fout * fin * 3, 256), 256, 0, s>>>(W, Wp, fout, fin, 0);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+int launch_unpermute_w(const float* Wp, float* W, int fout, int fin, cudaStream_t s) {
+  k_permute_w<<<cdiv(fout * fin * 3, 256), 256, 0, s>>>(Wp, W, fout, fin, 1);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t s) {
+  P2M_CUDA_OK(cudaMemsetAsync(p, 0, bytes, s));
+  return P2M_OK;
+}
+
+// =====================================================================================
+// BatchNorm1d over rows
+// =====================================================================================
+__global__ void k_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                               const float* bias, float* scale, float* shift, int F) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  float sc = gamma[c] / sqrtf(rv[c] + 1e-5f);
+  scale[c] = sc;
+  float b = bias ? bias[c] : 0.f;
+  shift[c] = beta[c] + (b - rm[c]) * sc;   // ((z + b) - rm) * sc + beta
+}
+int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv, const float* bias,
+                        float* scale, float* shift, int F, cudaStream_t s) {
+  k_bn_fold_eval<<<cdiv(F, 128), 128, 0, s>>>(gamma, beta, rm, rv, bias, scale, shift, F);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// per-channel sum / sum of squares.  Block = 256 threads = (F-lanes x row-lanes); fp32 partials over
+// <= ROWS_PER_BLOCK/rl rows, fp64 across blocks.
+constexpr int STAT_ROWS = 512;
+__global__ void __launch_bounds__(256) k_col_stats(const float* __restrict__ z, long long rows, int F,
+                                                   double* __restrict__ sums) {
+  extern __shared__ float sm[];  // [2][256]
+  const int lanes = min(F, 256);
+  const int rl = 256 / lanes;
+  const int fl = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+  const long long rbeg = (long long)blockIdx.x * STAT_ROWS;
+  const long long rend = min(rows, rbeg + STAT_ROWS);
+  for (int f = fl; f < F; f += lanes) {
+    float s = 0.f, q = 0.f;
+    if (rr < rl) {
+      for (long long r = rbeg + rr; r < rend; r += rl) {
+        float v = z[r * F + f];
+        s += v;
+        q = fmaf(v, v, q);
+      }
+    }
+    sm[threadIdx.x] = s;
+    sm[256 + threadIdx.x] = q;
+    __syncthreads();
+    if (rr == 0) {
+      for (int j = 1; j < rl; ++j) {
+        s += sm[j * lanes + fl];
+        q += sm[256 + j * lanes + fl];
+      }
+      atomicAdd(&sums[f], (double)s);
+      atomicAdd(&sums[F + f], (double)q);
+    }
+    __syncthreads();
+  }
+}
+int launch_col_stats(const float* z, int rows, int F, double* sums, cudaStream_t s) {
+  P2M_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
+  k_col_stats<<<cdiv(rows, STAT_ROWS), 256, 2 * 256 * sizeof(float), s>>>(z, rows, F, sums);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+__global__ void k_bn_finalize(const double* __restrict__ sums, long long rows, int F, const float* gamma,
+                              const float* beta, float* rm, float* rv, long long* nbt, float* save_mean,
+                              float* save_invstd, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= F) return;
+  double n = (double)rows;
+  double mean = sums[c] / n;
+  double var = sums[F + c] / n - mean * mean;
+  if (var < 0) var = 0;
+  float invstd = (float)(1.0 / sqrt(var + 1e-5));
+  if (rm) rm[c] = 0.9f * rm[c] + 0.1f * (float)mean;                                  // momentum 0.1
+  if (rv) rv[c] = 0.9f * rv[c] + 0.1f * (float)(rows > 1 ? var * n / (n - 1.0) : var);  // unbiased
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_invstd) save_invstd[c] = invstd;
+  float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+}
+int launch_bn_finalize(const double* sums, int rows, int F, const float* gamma, const float* beta, float* rm, float* rv,
+                       int64_t* nbt, float* save_mean, float* save_invstd, float* scale, float* shift, cudaStream_t s) {
+  k_bn_finalize<<<cdiv(F, 128), 128, 0, s>>>(sums, rows, F, gamma, beta, rm, rv, (long long*)nbt, save_mean,
+                                             save_invstd, scale, shift);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+__global__ void __launch_bounds__(256) k_affine_act(const float* __restrict__ z, long long rows, int F,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                    int relu, const float* __restrict__ res, int res_F, int res_unpool,
+                                                    const int* __restrict__ i0, const int* __restrict__ i1,
+                                                    const float* __restrict__ lam, float* __restrict__ a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * F) return;
+  long long r = idx / F;
+  int n = (int)(idx - r * F);
+  float v = z[idx];
+  if (scale) v = fmaf(v, scale[n], shift[n]);
+  if (relu) v = fmaxf(v, 0.f);
+  if (res) {
+    const float* rr = res + (res_unpool ? (r >> 1) : r) * res_F;
+    float l = lam[n];
+    v += (1.f - l) * rr[i0[n]] + l * rr[i1[n]];
+  }
+  a[idx] = v;
+}
+int launch_affine_act(const float* z, int rows, int F, const float* scale, const float* shift, int relu,
+                      const float* res, int res_F, int res_unpool, const InterpTable* it, float* a, cudaStream_t s) {
+  k_affine_act<<<cdiv((long long)rows * F, 256), 256, 0, s>>>(z, rows, F, scale, shift, relu, res, res_F, res_unpool,
+                                                             it ? it->i0 : nullptr, it ? it->i1 : nullptr,
+                                                             it ? it->lam : nullptr, a);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// BN + ReLU backward.  Pass 1: s1 = sum g', s2 = sum g' * zhat  with g' = g_a * [bn(z) > 0].
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ z, const float* __restrict__ g_a,
+                                                       long long rows, int F, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, int relu,
+                                                       double* __restrict__ sums) {
+  extern __shared__ float sm[];
+  const int lanes = min(F, 256);
+  const int rl = 256 / lanes;
+  const int fl = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+  const long long rbeg = (long long)blockIdx.x * STAT_ROWS;
+  const long long rend = min(rows, rbeg + STAT_ROWS);
+  for (int f = fl; f < F; f += lanes) {
+    float s = 0.f, q = 0.f;
+    if (rr < rl) {
+      float mu = mean[f], is = invstd[f], ga = gamma[f], be = beta[f];
+      for (long long r = rbeg + rr; r < rend; r += rl) {
+        float zh = (z[r * F + f] - mu) * is;
+        float g = g_a[r * F + f];
+        if (relu && !(fmaf(zh, ga, be) > 0.f)) g = 0.f;
+        s += g;
+        q = fmaf(g, zh, q);
+      }
+    }
+    sm[threadIdx.x] = s;
+    sm[256 + threadIdx.x] = q;
+    __syncthreads();
+    if (rr == 0) {
+      for (int j = 1; j < rl; ++j) {
+        s += sm[j * lanes + fl];
+        q += sm[256 + j * lanes + fl];
+      }
+      atomicAdd(&sums[f], (double)s);
+      atomicAdd(&sums[F + f], (double)q);
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ z, const float* __restrict__ g_a,
+                                                      long long rows, int F, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, int relu,
+                                                      const double* __restrict__ sums, float* __restrict__ dgamma,
+                                                      float* __restrict__ dbeta, float* __restrict__ g_z) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < F) {
+    dbeta[idx] = (float)sums[idx];
+    dgamma[idx] = (float)sums[F + idx];
+  }
+  if (idx >= rows * F) return;
+  int f = (int)(idx % F);
+  float zh = (z[idx] - mean[f]) * invstd[f];
+  float g = g_a[idx];
+  if (relu && !(fmaf(zh, gamma[f], beta[f]) > 0.f)) g = 0.f;
+  float m1 = (float)(sums[f] / (double)rows);
+  float m2 = (float)(sums[F + f] / (double)rows);
+  g_z[idx] = gamma[f] * invstd[f] * (g - m1 - zh * m2);
+}
+int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* beta,
+                        const float* mean, const float* invstd, int relu, double* sums, float* dgamma, float* dbeta,
+                        float* g_z, cudaStream_t s) {
+  P2M_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
+  k_bn_bwd_reduce<<<cdiv(rows, STAT_ROWS), 256, 2 * 256 * sizeof(float), s>>>(z, g_a, rows, F, gamma, beta, mean,
+                                                                               invstd, relu, sums);
+  P2M_LAUNCH_OK();
+  k_bn_bwd_apply<<<cdiv((long long)rows * F, 256), 256, 0, s>>>(z, g_a, rows, F, gamma, beta, mean, invstd, relu, sums,
+                                                               dgamma, dbeta, g_z);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+__global__ void __launch_bounds__(256) k_col_sum(const float* __restrict__ g, long long rows, int F,
+                                                 double* __restrict__ sums) {
+  extern __shared__ float sm[];
+  const int lanes = min(F, 256);
+  const int rl = 256 / lanes;
+  const int fl = threadIdx.x % lanes, rr = threadIdx.x / lanes;
+  const long long rbeg = (long long)blockIdx.x * STAT_ROWS;
+  const long long rend = min(rows, rbeg + STAT_ROWS);
+  for (int f = fl; f < F; f += lanes) {
+    float s = 0.f;
+    if (rr < rl)
+      for (long long r = rbeg + rr; r < rend; r += rl) s += g[r * F + f];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (rr == 0) {
+      for (int j = 1; j < rl; ++j) s += sm[j * lanes + fl];
+      atomicAdd(&sums[f], (double)s);
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_d2f(const double* in, float* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+int launch_col_sum(const float* g, int rows, int F, double* scratch, float* out, cudaStream_t s) {
+  P2M_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * F, s));
+  k_col_sum<<<cdiv(rows, STAT_ROWS), 256, 256 * sizeof(float), s>>>(g, rows, F, scratch);
+  P2M_LAUNCH_OK();
+  k_d2f<<<cdiv(F, 128), 128, 0, s>>>(scratch, out, F);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+}  // namespace p2m

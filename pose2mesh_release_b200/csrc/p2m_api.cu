@@ -1,0 +1,764 @@
+// C-ABI layer (include/p2m_b200.h): model handle, workspace planning and the forward / backward
+// schedules of Pose2Mesh.forward (lib/models/meshnet.py:80-117 of the reference), expressed as
+// sequences of the kernels in kernels_simt.cu / cheb_umma.cu on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "p2m_internal.h"
+
+namespace p2m {
+
+static thread_local std::string g_error;
+static thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+void count_launch(int n) { g_launches += n; }
+
+struct Layer {
+  int level, V, fin, fout;
+  int bn, relu;
+  int block, pos, block_end;
+};
+
+struct Block {
+  int first_layer, n_layers;
+  int level;
+  int has_residual;   // 1 <= b <= nb-2   (meshnet.py:108-115)
+  int out_unpool;     // 1 <= b <  nb-2   (meshnet.py:111)
+  int in_unpool;      // input of this block is the (virtually) unpooled output of the previous block
+  int cin, cout;
+  InterpTable interp;  // valid when has_residual
+};
+
+}  // namespace p2m
+
+using namespace p2m;
+
+struct p2m_model {
+  int device = 0;
+  int sm_count = 148;
+  int precision = P2M_PREC_FP32_SIMT;
+  std::vector<DevLevel> levels;
+  std::vector<Layer> layers;
+  std::vector<Block> blocks;
+  int n_joint = 0, cin = 0, cout = 0;
+  int fc_in = 0, fc_out = 0;
+  std::vector<void*> owned;  // device allocations to free
+};
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+inline size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+struct Bump {
+  char* base;
+  size_t off = 0;
+  explicit Bump(void* p) : base(static_cast<char*>(p)) {}
+  template <class T>
+  T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return p;
+  }
+};
+
+template <class T>
+int upload(p2m_model* m, const std::vector<T>& h, T** out) {
+  T* d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  P2M_CUDA_OK(cudaMalloc(&d, bytes));
+  m->owned.push_back(d);
+  if (!h.empty()) P2M_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return P2M_OK;
+}
+
+// F.interpolate(x, size=fout, mode='linear', align_corners=False) along the channel axis
+// (meshnet.py:109,114; ATen upsample_linear1d: src = scale*(j+0.5)-0.5 clamped at 0, scale = fin/fout).
+int build_interp(p2m_model* m, int fin, int fout, InterpTable* t) {
+  t->fin = fin;
+  t->fout = fout;
+  std::vector<int> i0(fout), i1(fout);
+  std::vector<float> lam(fout);
+  const float scale = (float)fin / (float)fout;
+  for (int j = 0; j < fout; ++j) {
+    float src = scale * ((float)j + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int a = (int)src;
+    if (a > fin - 1) a = fin - 1;
+    int b = a + ((a < fin - 1) ? 1 : 0);
+    i0[j] = a;
+    i1[j] = b;
+    lam[j] = src - (float)a;
+  }
+  std::vector<int> tp(fin + 1, 0), ti;
+  std::vector<float> tw;
+  for (int i = 0; i < fin; ++i) {
+    for (int j = 0; j < fout; ++j) {
+      float w = 0.f;
+      if (i0[j] == i) w += 1.f - lam[j];
+      if (i1[j] == i) w += lam[j];
+      if (w != 0.f) {
+        ti.push_back(j);
+        tw.push_back(w);
+      }
+    }
+    tp[i + 1] = (int)ti.size();
+  }
+  P2M_TRY(upload(m, i0, &t->i0));
+  P2M_TRY(upload(m, i1, &t->i1));
+  P2M_TRY(upload(m, lam, &t->lam));
+  P2M_TRY(upload(m, tp, &t->t_ptr));
+  P2M_TRY(upload(m, ti, &t->t_idx));
+  P2M_TRY(upload(m, tw, &t->t_w));
+  return P2M_OK;
+}
+
+struct Sizes {
+  size_t max_act = 0;    // floats: max over layers of rows*fout (and fc in/out, and x)
+  size_t max_T = 0;      // floats: max rows*3*fin
+  size_t max_U = 0;      // floats: max rows*fin
+  size_t max_w = 0;      // floats: max fout*3*fin
+  int max_f = 0;
+};
+
+Sizes model_sizes(const p2m_model* m, int B) {
+  Sizes s;
+  for (const Layer& L : m->layers) {
+    size_t rows = (size_t)B * L.V;
+    s.max_act = std::max(s.max_act, rows * L.fout);
+    s.max_act = std::max(s.max_act, rows * L.fin);
+    s.max_T = std::max(s.max_T, rows * 3 * L.fin);
+    s.max_U = std::max(s.max_U, rows * L.fin);
+    s.max_w = std::max(s.max_w, (size_t)L.fout * 3 * L.fin);
+    s.max_f = std::max(s.max_f, std::max(L.fin, L.fout));
+  }
+  s.max_act = std::max(s.max_act, (size_t)B * m->fc_out);
+  s.max_act = std::max(s.max_act, (size_t)B * m->fc_in);
+  return s;
+}
+
+// Workspace map shared by forward and backward (deterministic bump order).
+struct WsMap {
+  float* T;
+  float* wp_scratch;
+  float* scale_scratch;   // [2*max_f] eval folded scale/shift
+  double* sums;           // [2*max_f]
+  float* rot[3];          // eval: rotating activation buffers
+  // training: saved tensors
+  std::vector<float*> z, a, mean, invstd, scale, shift, wp;
+  float* fc_out = nullptr;
+  size_t bytes = 0;
+};
+
+WsMap map_workspace(const p2m_model* m, int B, int training, void* base) {
+  WsMap w;
+  Sizes s = model_sizes(m, B);
+  Bump b(base);
+  w.T = b.take<float>(s.max_T);
+  w.wp_scratch = b.take<float>(s.max_w);
+  w.scale_scratch = b.take<float>(2 * (size_t)s.max_f);
+  w.sums = b.take<double>(2 * (size_t)s.max_f);
+  const size_t nl = m->layers.size();
+  if (!training) {
+    for (int i = 0; i < 3; ++i) w.rot[i] = b.take<float>(s.max_act);
+  } else {
+    w.rot[0] = w.rot[1] = w.rot[2] = nullptr;
+    w.z.resize(nl); w.a.resize(nl); w.mean.resize(nl); w.invstd.resize(nl);
+    w.scale.resize(nl); w.shift.resize(nl); w.wp.resize(nl);
+    for (size_t i = 0; i < nl; ++i) {
+      const Layer& L = m->layers[i];
+      size_t n = (size_t)B * L.V * L.fout;
+      w.wp[i] = b.take<float>((size_t)L.fout * 3 * L.fin);
+      if (L.bn) {
+        w.z[i] = b.take<float>(n);
+        w.a[i] = b.take<float>(n);
+        w.mean[i] = b.take<float>(L.fout);
+        w.invstd[i] = b.take<float>(L.fout);
+        w.scale[i] = b.take<float>(L.fout);
+        w.shift[i] = b.take<float>(L.fout);
+      } else {
+        w.z[i] = w.a[i] = nullptr;  // last layer writes y directly
+        w.mean[i] = w.invstd[i] = w.scale[i] = w.shift[i] = nullptr;
+      }
+    }
+    w.fc_out = b.take<float>((size_t)B * m->fc_out);
+  }
+  w.bytes = b.off;
+  return w;
+}
+
+struct BwdMap {
+  float* G[4];
+  float* U;
+  float* dwp;
+  double* sums;
+  size_t bytes;
+};
+BwdMap map_scratch(const p2m_model* m, int B, void* base) {
+  BwdMap w;
+  Sizes s = model_sizes(m, B);
+  Bump b(base);
+  for (int i = 0; i < 4; ++i) w.G[i] = b.take<float>(s.max_act);
+  w.U = b.take<float>(s.max_U);
+  w.dwp = b.take<float>(std::max(s.max_w, (size_t)1));
+  w.sums = b.take<double>(2 * (size_t)s.max_f + 2 * (size_t)m->fc_out);
+  w.bytes = b.off;
+  return w;
+}
+
+// ---- one conv layer, linear part + epilogue -------------------------------------------------
+// y = epilogue( [T0|T1|T2](x) * Wp^T )
+int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpool, const float* w_ref, float* T,
+                float* wp, const Epilogue& ep, float* y, cudaStream_t s) {
+  const int rows = B * L.V;
+  const DevLevel& g = m->levels[L.level];
+  P2M_TRY(launch_permute_w(w_ref, wp, L.fout, L.fin, s));
+  P2M_TRY(launch_cheb_basis(g, x, in_unpool, rows, L.fin, T, s));
+  P2M_TRY(launch_gemm(T, 3 * L.fin, wp, 3 * L.fin, 0, y, L.fout, rows, L.fout, 3 * L.fin, ep, s));
+  return P2M_OK;
+}
+
+int check_params(const p2m_model* m, const p2m_params_t* p, bool need_running) {
+  if (!p || !p->fc_w || !p->fc_b || !p->cl_w || !p->cl_b || !p->bn_w || !p->bn_b) {
+    set_error("params: null table");
+    return P2M_ERR_INVALID;
+  }
+  for (size_t i = 0; i < m->layers.size(); ++i) {
+    if (!p->cl_w[i] || !p->cl_b[i]) {
+      set_error("params: null conv weight/bias for layer " + std::to_string(i));
+      return P2M_ERR_INVALID;
+    }
+    if (m->layers[i].bn) {
+      if (!p->bn_w[i] || !p->bn_b[i] || (need_running && (!p->bn_rm || !p->bn_rv || !p->bn_rm[i] || !p->bn_rv[i]))) {
+        set_error("params: null BatchNorm tensor for layer " + std::to_string(i));
+        return P2M_ERR_INVALID;
+      }
+    }
+  }
+  return P2M_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char* p2m_last_error(void) { return g_error.c_str(); }
+const char* p2m_version(void) { return "pose2mesh_release_b200 0.1 (sm_100a)"; }
+int64_t p2m_launch_count(void) { return g_launches; }
+void p2m_launch_count_reset(void) { g_launches = 0; }
+
+int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
+  if (!d || !out || d->n_levels < 1 || (d->n_blocks != 0 && (d->n_blocks < 3 || d->n_levels < 2))) {
+    set_error("model_create: bad descriptor");
+    return P2M_ERR_INVALID;
+  }
+  // n_blocks == 0: graph-only handle (levels without a channel plan) for the single-layer entry points
+  if (d->n_blocks != 0 && d->n_levels != d->n_blocks - 1) {
+    set_error("model_create: need n_levels == n_blocks - 1 (one level per block; the last block re-uses the finest)");
+    return P2M_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || d->device >= ndev) {
+    set_error("model_create: no usable CUDA device (this library has no CPU path)");
+    cudaGetLastError();
+    return P2M_ERR_NOGPU;
+  }
+  cudaDeviceProp prop;
+  P2M_CUDA_OK(cudaGetDeviceProperties(&prop, d->device));
+  if (prop.major != 10) {
+    set_error(std::string("model_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+              ", this library is built for sm_100a only");
+    return P2M_ERR_NOGPU;
+  }
+  P2M_CUDA_OK(cudaSetDevice(d->device));
+  p2m_model* m = new p2m_model();
+  m->device = d->device;
+  m->sm_count = prop.multiProcessorCount;
+  // ---- levels: CSR with relative offsets
+  for (int l = 0; l < d->n_levels; ++l) {
+    DevLevel g;
+    g.V = d->level_size[l];
+    const int32_t* rp = d->rowptr[l];
+    g.nnz = rp[g.V];
+    std::vector<int> rowptr(rp, rp + g.V + 1), rel(g.nnz);
+    std::vector<float> val(d->values[l], d->values[l] + g.nnz);
+    for (int v = 0; v < g.V; ++v) {
+      g.max_row_nnz = std::max(g.max_row_nnz, rp[v + 1] - rp[v]);
+      for (int p = rp[v]; p < rp[v + 1]; ++p) {
+        int c = d->colidx[l][p];
+        if (c < 0 || c >= g.V) {
+          set_error("model_create: column index out of range");
+          p2m_model_destroy(m);
+          return P2M_ERR_INVALID;
+        }
+        rel[p] = c - v;
+      }
+    }
+    int st;
+    if ((st = upload(m, rowptr, &g.rowptr)) || (st = upload(m, rel, &g.reloff)) || (st = upload(m, val, &g.val))) {
+      p2m_model_destroy(m);
+      return st;
+    }
+    m->levels.push_back(g);
+  }
+  // ---- plan (meshnet.py:21-33, 86-94)
+  const int nb = d->n_blocks;
+  int off = 0, li = 0;
+  for (int b = 0; b < nb; ++b) {
+    const int32_t* ch = d->block_chans + off;
+    const int len = d->block_len[b];
+    if (len < 2) {
+      set_error("model_create: block with < 2 channel entries");
+      p2m_model_destroy(m);
+      return P2M_ERR_INVALID;
+    }
+    Block blk{};
+    blk.first_layer = li;
+    blk.n_layers = len - 1;
+    blk.level = (b == nb - 1) ? 0 : d->n_levels - 1 - b;
+    blk.has_residual = (b >= 1 && b <= nb - 2);
+    blk.out_unpool = (b >= 1 && b < nb - 2);
+    blk.in_unpool = (b >= 2 && b <= nb - 2);
+    blk.cin = ch[0];
+    blk.cout = ch[len - 1];
+    for (int j = 0; j < len - 1; ++j) {
+      Layer L{};
+      L.level = blk.level;
+      L.V = m->levels[L.level].V;
+      L.fin = ch[j];
+      L.fout = ch[j + 1];
+      const bool last = (b == nb - 1) && (j == len - 2);
+      L.bn = !last;
+      L.relu = !last;
+      L.block = b;
+      L.pos = j;
+      L.block_end = (j == len - 2);
+      m->layers.push_back(L);
+      ++li;
+    }
+    if (blk.has_residual) {
+      int st = build_interp(m, blk.cin, blk.cout, &blk.interp);
+      if (st) {
+        p2m_model_destroy(m);
+        return st;
+      }
+    }
+    m->blocks.push_back(blk);
+    off += len;
+  }
+  // consistency: unpool doubles the level size; block b+1 input channels == block b output channels
+  for (int b = 1; b < nb; ++b) {
+    const Block& p = m->blocks[b - 1];
+    const Block& c = m->blocks[b];
+    bool ok = (c.cin == p.cout);
+    if (b >= 2) {
+      int vp = m->levels[p.level].V, vc = m->levels[c.level].V;
+      ok = ok && (p.out_unpool ? (vc == 2 * vp) : (vc == vp));
+    }
+    if (!ok) {
+      set_error("model_create: inconsistent hierarchy / channel plan at block " + std::to_string(b));
+      p2m_model_destroy(m);
+      return P2M_ERR_INVALID;
+    }
+  }
+  if (nb == 0) {
+    *out = m;
+    return P2M_OK;
+  }
+  m->n_joint = m->levels.back().V;
+  m->cin = m->blocks[0].cin;
+  m->cout = m->blocks[nb - 1].cout;
+  m->fc_in = m->n_joint * m->blocks[0].cout;
+  m->fc_out = m->levels[m->blocks[1].level].V * m->blocks[1].cin;
+  *out = m;
+  return P2M_OK;
+}
+
+void p2m_model_destroy(p2m_model_t* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (void* p : m->owned) cudaFree(p);
+  delete m;
+}
+
+int p2m_model_num_layers(const p2m_model_t* m) { return m ? (int)m->layers.size() : 0; }
+
+int p2m_model_layer_info(const p2m_model_t* m, int layer, int32_t out[6]) {
+  if (!m || layer < 0 || layer >= (int)m->layers.size()) {
+    set_error("layer_info: bad layer");
+    return P2M_ERR_INVALID;
+  }
+  const Layer& L = m->layers[layer];
+  out[0] = L.level; out[1] = L.V; out[2] = L.fin; out[3] = L.fout; out[4] = L.bn; out[5] = L.relu;
+  return P2M_OK;
+}
+
+int p2m_model_set_precision(p2m_model_t* m, int precision) {
+  if (!m || (precision != P2M_PREC_FP32_SIMT && precision != P2M_PREC_FP16X3_TC)) {
+    set_error("set_precision: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  m->precision = precision;
+  return P2M_OK;
+}
+
+size_t p2m_meshnet_workspace_bytes(const p2m_model_t* m, int batch, int training) {
+  if (!m || batch <= 0 || m->layers.empty()) return 0;
+  return map_workspace(m, batch, training, nullptr).bytes;
+}
+size_t p2m_meshnet_backward_scratch_bytes(const p2m_model_t* m, int batch) {
+  if (!m || batch <= 0 || m->layers.empty()) return 0;
+  return map_scratch(m, batch, nullptr).bytes;
+}
+size_t p2m_meshnet_host_io_bytes(const p2m_model_t* m, int batch) {
+  if (!m || batch <= 0 || m->layers.empty()) return 0;
+  return align_up((size_t)batch * m->n_joint * m->cin * 4) + align_up((size_t)batch * m->levels[0].V * m->cout * 4);
+}
+
+// -------------------------------------------------------------------------------------
+int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, float* y, int B, int training,
+                        void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  if (!m || !x || !y || B <= 0 || !workspace || m->layers.empty()) {
+    set_error("meshnet_forward: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  P2M_TRY(check_params(m, P, true));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WsMap w = map_workspace(m, B, training, workspace);
+  if (w.bytes > workspace_bytes) {
+    set_error("meshnet_forward: workspace too small (" + std::to_string(workspace_bytes) + " < " +
+              std::to_string(w.bytes) + ")");
+    return P2M_ERR_WORKSPACE;
+  }
+  const int nb = (int)m->blocks.size();
+  const int nl = (int)m->layers.size();
+  const float* cur = x;
+  int cur_unpool = 0;
+  int cur_buf = -1;  // rotating buffer id holding `cur` (eval)
+  for (int b = 0; b < nb; ++b) {
+    const Block& blk = m->blocks[b];
+    const float* block_in = cur;
+    const int block_in_unpool = cur_unpool;
+    const int block_in_buf = cur_buf;
+    for (int j = 0; j < blk.n_layers; ++j) {
+      const int li = blk.first_layer + j;
+      const Layer& L = m->layers[li];
+      const int rows = B * L.V;
+      const bool last = (li == nl - 1);
+      const bool with_res = L.block_end && blk.has_residual;
+      if (!training) {
+        Epilogue ep;
+        float* scale = w.scale_scratch;
+        float* shift = w.scale_scratch + L.fout;
+        if (L.bn) {
+          P2M_TRY(launch_bn_fold_eval(P->bn_w[li], P->bn_b[li], P->bn_rm[li], P->bn_rv[li], P->cl_b[li], scale, shift,
+                                      L.fout, s));
+          ep.scale = scale;
+          ep.shift = shift;
+        } else {
+          ep.bias = P->cl_b[li];
+        }
+        ep.relu = L.relu;
+        if (with_res) {
+          ep.res = block_in;
+          ep.res_F = blk.cin;
+          ep.res_unpool = block_in_unpool;
+          ep.res_i0 = blk.interp.i0;
+          ep.res_i1 = blk.interp.i1;
+          ep.res_lam = blk.interp.lam;
+        }
+        float* out;
+        int out_buf = -1;
+        if (last) {
+          out = y;
+        } else {
+          for (int c = 0; c < 3; ++c)
+            if (c != cur_buf && c != block_in_buf) {
+              out_buf = c;
+              break;
+            }
+          out = w.rot[out_buf];
+        }
+        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, ep, out, s));
+        cur = out;
+        cur_buf = out_buf;
+        cur_unpool = 0;
+      } else {
+        Epilogue ep;
+        ep.bias = P->cl_b[li];
+        float* z = last ? y : w.z[li];
+        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp[li], ep, z, s));
+        if (L.bn) {
+          P2M_TRY(launch_col_stats(z, rows, L.fout, w.sums, s));
+          P2M_TRY(launch_bn_finalize(w.sums, rows, L.fout, P->bn_w[li], P->bn_b[li], P->bn_rm[li], P->bn_rv[li],
+                                     P->bn_nbt ? P->bn_nbt[li] : nullptr, w.mean[li], w.invstd[li], w.scale[li],
+                                     w.shift[li], s));
+          P2M_TRY(launch_affine_act(z, rows, L.fout, w.scale[li], w.shift[li], L.relu, with_res ? block_in : nullptr,
+                                    blk.cin, block_in_unpool, with_res ? &blk.interp : nullptr, w.a[li], s));
+          cur = w.a[li];
+        } else {
+          cur = z;
+        }
+        cur_unpool = 0;
+      }
+    }
+    if (b == 0) {  // fc: joints -> coarsest mesh level (meshnet.py:104-106)
+      Epilogue ep;
+      ep.bias = P->fc_b;
+      float* out;
+      if (!training) {
+        int out_buf = -1;
+        for (int c = 0; c < 3; ++c)
+          if (c != cur_buf) {
+            out_buf = c;
+            break;
+          }
+        out = w.rot[out_buf];
+        cur_buf = out_buf;
+      } else {
+        out = w.fc_out;
+      }
+      P2M_TRY(launch_gemm(cur, m->fc_in, P->fc_w, m->fc_in, 0, out, m->fc_out, B, m->fc_out, m->fc_in, ep, s));
+      cur = out;
+      cur_unpool = 0;
+    } else if (blk.out_unpool) {
+      cur_unpool = 1;  // nearest x2 unpool is virtual: the next block reads row r>>1
+    }
+  }
+  return P2M_OK;
+}
+
+int p2m_meshnet_forward_host(p2m_model_t* m, const p2m_params_t* P, const float* x_host, float* y_host, int B,
+                             void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  if (!m || !x_host || !y_host || B <= 0 || !workspace || m->layers.empty()) {
+    set_error("meshnet_forward_host: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t xb = (size_t)B * m->n_joint * m->cin * 4, yb = (size_t)B * m->levels[0].V * m->cout * 4;
+  const size_t io = p2m_meshnet_host_io_bytes(m, B);
+  const size_t need = p2m_meshnet_workspace_bytes(m, B, 0);
+  if (workspace_bytes < need + io) {
+    set_error("meshnet_forward_host: workspace too small");
+    return P2M_ERR_WORKSPACE;
+  }
+  char* base = static_cast<char*>(workspace);
+  float* xd = reinterpret_cast<float*>(base + need);
+  float* yd = reinterpret_cast<float*>(base + need + align_up(xb));
+  P2M_CUDA_OK(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, s));
+  P2M_TRY(p2m_meshnet_forward(m, P, xd, yd, B, 0, workspace, need, stream));
+  P2M_CUDA_OK(cudaMemcpyAsync(y_host, yd, yb, cudaMemcpyDeviceToHost, s));
+  P2M_CUDA_OK(cudaStreamSynchronize(s));
+  return P2M_OK;
+}
+
+// -------------------------------------------------------------------------------------
+int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params_t* G, const float* x, const float* dy,
+                         float* dx, int B, void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                         p2m_stream_t stream) {
+  if (!m || !x || !dy || B <= 0 || !workspace || !scratch || m->layers.empty()) {
+    set_error("meshnet_backward: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  P2M_TRY(check_params(m, P, false));
+  P2M_TRY(check_params(m, G, false));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  WsMap w = map_workspace(m, B, 1, workspace);
+  BwdMap sc = map_scratch(m, B, scratch);
+  if (w.bytes > workspace_bytes || sc.bytes > scratch_bytes) {
+    set_error("meshnet_backward: workspace/scratch too small");
+    return P2M_ERR_WORKSPACE;
+  }
+  const int nb = (int)m->blocks.size();
+  const float* g_cur = dy;
+  int g_cur_buf = -2;  // -2: external (dy)
+  int keep_buf = -1;   // buffer holding g_out of the block being processed (residual path)
+  const float* keep_ptr = nullptr;
+  auto free_buf = [&](int a, int b2, int c) {
+    for (int i = 0; i < 4; ++i)
+      if (i != a && i != b2 && i != c) return i;
+    return -1;
+  };
+  for (int b = nb - 1; b >= 0; --b) {
+    const Block& blk = m->blocks[b];
+    // input of this block (physical tensor + unpool flag)
+    const float* block_in;
+    if (b == 0)
+      block_in = x;
+    else if (b == 1)
+      block_in = w.fc_out;
+    else
+      block_in = w.a[m->blocks[b - 1].first_layer + m->blocks[b - 1].n_layers - 1];
+    for (int j = blk.n_layers - 1; j >= 0; --j) {
+      const int li = blk.first_layer + j;
+      const Layer& L = m->layers[li];
+      const DevLevel& g = m->levels[L.level];
+      const int rows = B * L.V;
+      const float* inp = (j == 0) ? block_in : w.a[li - 1];
+      const int in_unpool = (j == 0) ? blk.in_unpool : 0;
+      const float* g_z = g_cur;
+      int gz_buf = g_cur_buf;
+      if (L.block_end && blk.has_residual) {
+        keep_buf = g_cur_buf;
+        keep_ptr = g_cur;
+      }
+      if (L.bn) {
+        int tgt = (g_cur_buf >= 0 && g_cur_buf != keep_buf) ? g_cur_buf : free_buf(g_cur_buf, keep_buf, -1);
+        P2M_TRY(launch_bn_relu_bwd(w.z[li], g_cur, rows, L.fout, P->bn_w[li], P->bn_b[li], w.mean[li], w.invstd[li],
+                                   L.relu, sc.sums, G->bn_w[li], G->bn_b[li], sc.G[tgt], s));
+        g_z = sc.G[tgt];
+        gz_buf = tgt;
+      }
+      P2M_TRY(launch_col_sum(g_z, rows, L.fout, sc.sums, G->cl_b[li], s));
+      // dW: recompute the basis of the layer input, dWp = g_z^T T
+      P2M_TRY(launch_cheb_basis(g, inp, in_unpool, rows, L.fin, w.T, s));
+      P2M_TRY(launch_fill_zero(sc.dwp, sizeof(float) * L.fout * 3 * L.fin, s));
+      P2M_TRY(launch_gemm_tn_atomic(g_z, L.fout, w.T, 3 * L.fin, sc.dwp, 3 * L.fin, rows, L.fout, 3 * L.fin, s));
+      P2M_TRY(launch_unpermute_w(sc.dwp, G->cl_w[li], L.fout, L.fin, s));
+      // dX
+      const bool need_dx = !(li == 0 && dx == nullptr);
+      if (need_dx) {
+        Epilogue none;
+        P2M_TRY(launch_gemm(g_z, L.fout, w.wp[li], 3 * L.fin, 1, w.T, 3 * L.fin, rows, 3 * L.fin, L.fout, none, s));
+        const bool res_here = (j == 0) && blk.has_residual;
+        float* out;
+        int out_buf = -1;
+        if (li == 0) {
+          out = dx;
+        } else {
+          out_buf = free_buf(gz_buf, keep_buf, -1);
+          out = sc.G[out_buf];
+        }
+        P2M_TRY(launch_cheb_basis_bwd(g, w.T, rows, L.fin, sc.U, res_here ? keep_ptr : nullptr, blk.cout,
+                                      res_here ? &blk.interp : nullptr, in_unpool, out, s));
+        g_cur = out;
+        g_cur_buf = out_buf;
+      }
+      if (j == 0) {
+        keep_buf = -1;
+        keep_ptr = nullptr;
+      }
+    }
+    if (b == 1) {  // fc backward (meshnet.py:104-106)
+      const float* a0 = w.a[m->blocks[0].first_layer + m->blocks[0].n_layers - 1];  // [B, fc_in]
+      P2M_TRY(launch_col_sum(g_cur, B, m->fc_out, sc.sums, G->fc_b, s));
+      P2M_TRY(launch_fill_zero(G->fc_w, sizeof(float) * (size_t)m->fc_out * m->fc_in, s));
+      P2M_TRY(launch_gemm_tn_atomic(g_cur, m->fc_out, a0, m->fc_in, G->fc_w, m->fc_in, B, m->fc_out, m->fc_in, s));
+      int out_buf = free_buf(g_cur_buf, -1, -1);
+      Epilogue none;
+      P2M_TRY(launch_gemm(g_cur, m->fc_out, P->fc_w, m->fc_in, 1, sc.G[out_buf], m->fc_in, B, m->fc_in, m->fc_out, none, s));
+      g_cur = sc.G[out_buf];
+      g_cur_buf = out_buf;
+    }
+  }
+  return P2M_OK;
+}
+
+// -------------------------------------------------------------------------------------
+size_t p2m_cheb_conv_workspace_bytes(const p2m_model_t* m, int level, int batch, int fin, int fout) {
+  if (!m || level < 0 || level >= (int)m->levels.size()) return 0;
+  size_t rows = (size_t)batch * m->levels[level].V;
+  return align_up(rows * 3 * fin * 4) + align_up((size_t)fout * 3 * fin * 4) * 2 + align_up(rows * fin * 4) +
+         align_up(rows * fout * 4) + align_up(2 * (size_t)std::max(fin, fout) * 8) + align_up(2 * (size_t)fout * 4) + ALIGN;
+}
+
+int p2m_cheb_conv_fwd(p2m_model_t* m, const p2m_conv_fwd_args_t* a, void* workspace, size_t workspace_bytes,
+                      p2m_stream_t stream) {
+  if (!m || !a || !a->x || !a->weight || !a->bias || !a->y || a->level < 0 || a->level >= (int)m->levels.size()) {
+    set_error("cheb_conv_fwd: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  if (workspace_bytes < p2m_cheb_conv_workspace_bytes(m, a->level, a->batch, a->fin, a->fout)) {
+    set_error("cheb_conv_fwd: workspace too small");
+    return P2M_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Layer L{};
+  L.level = a->level;
+  L.V = m->levels[a->level].V;
+  L.fin = a->fin;
+  L.fout = a->fout;
+  const size_t rows = (size_t)a->batch * L.V;
+  Bump b(workspace);
+  float* T = b.take<float>(rows * 3 * L.fin);
+  float* wp = b.take<float>((size_t)L.fout * 3 * L.fin);
+  b.take<float>((size_t)L.fout * 3 * L.fin);
+  b.take<float>(rows * L.fin);
+  float* z = b.take<float>(rows * L.fout);
+  double* sums = b.take<double>(2 * (size_t)std::max(L.fin, L.fout));
+  float* sc = b.take<float>(2 * (size_t)L.fout);
+  Epilogue ep;
+  if (a->bn_mode == 0) {
+    ep.bias = a->bias;
+    ep.relu = a->relu;
+    return conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, ep, a->y, s);
+  }
+  if (!a->bn_weight || !a->bn_bias) {
+    set_error("cheb_conv_fwd: BatchNorm parameters missing");
+    return P2M_ERR_INVALID;
+  }
+  if (a->bn_mode == 1) {
+    if (!a->bn_running_mean || !a->bn_running_var) {
+      set_error("cheb_conv_fwd: running stats missing");
+      return P2M_ERR_INVALID;
+    }
+    P2M_TRY(launch_bn_fold_eval(a->bn_weight, a->bn_bias, a->bn_running_mean, a->bn_running_var, a->bias, sc,
+                                sc + L.fout, L.fout, s));
+    ep.scale = sc;
+    ep.shift = sc + L.fout;
+    ep.relu = a->relu;
+    return conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, ep, a->y, s);
+  }
+  ep.bias = a->bias;
+  P2M_TRY(conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, ep, z, s));
+  P2M_TRY(launch_col_stats(z, (int)rows, L.fout, sums, s));
+  P2M_TRY(launch_bn_finalize(sums, (int)rows, L.fout, a->bn_weight, a->bn_bias, a->bn_running_mean, a->bn_running_var,
+                             a->bn_num_batches_tracked, a->save_mean, a->save_invstd, sc, sc + L.fout, s));
+  P2M_TRY(launch_affine_act(z, (int)rows, L.fout, sc, sc + L.fout, a->relu, nullptr, 0, 0, nullptr, a->y, s));
+  return P2M_OK;
+}
+
+int p2m_cheb_conv_bwd(p2m_model_t* m, const p2m_conv_bwd_args_t* a, void* workspace, size_t workspace_bytes,
+                      p2m_stream_t stream) {
+  if (!m || !a || !a->x || !a->weight || !a->dz || !a->dweight || !a->dbias || a->level < 0 ||
+      a->level >= (int)m->levels.size()) {
+    set_error("cheb_conv_bwd: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  if (workspace_bytes < p2m_cheb_conv_workspace_bytes(m, a->level, a->batch, a->fin, a->fout)) {
+    set_error("cheb_conv_bwd: workspace too small");
+    return P2M_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const DevLevel& g = m->levels[a->level];
+  const int fin = a->fin, fout = a->fout;
+  const size_t rows = (size_t)a->batch * g.V;
+  Bump b(workspace);
+  float* T = b.take<float>(rows * 3 * fin);
+  float* wp = b.take<float>((size_t)fout * 3 * fin);
+  float* dwp = b.take<float>((size_t)fout * 3 * fin);
+  float* U = b.take<float>(rows * fin);
+  b.take<float>(rows * fout);
+  double* sums = b.take<double>(2 * (size_t)std::max(fin, fout));
+  P2M_TRY(launch_col_sum(a->dz, (int)rows, fout, sums, a->dbias, s));
+  P2M_TRY(launch_cheb_basis(g, a->x, 0, (int)rows, fin, T, s));
+  P2M_TRY(launch_fill_zero(dwp, sizeof(float) * fout * 3 * fin, s));
+  P2M_TRY(launch_gemm_tn_atomic(a->dz, fout, T, 3 * fin, dwp, 3 * fin, (int)rows, fout, 3 * fin, s));
+  P2M_TRY(launch_unpermute_w(dwp, a->dweight, fout, fin, s));
+  if (a->dx) {
+    Epilogue none;
+    P2M_TRY(launch_permute_w(a->weight, wp, fout, fin, s));
+    P2M_TRY(launch_gemm(a->dz, fout, wp, 3 * fin, 1, T, 3 * fin, (int)rows, 3 * fin, fout, none, s));
+    P2M_TRY(launch_cheb_basis_bwd(g, T, (int)rows, fin, U, nullptr, 0, nullptr, 0, a->dx, s));
+  }
+  return P2M_OK;
+}
+
+}  // extern "C"

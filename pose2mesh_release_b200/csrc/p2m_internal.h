@@ -1,0 +1,136 @@
+// Internal (C++) interface between the C-ABI layer (p2m_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/p2m_b200.h"
+
+namespace p2m {
+
+// ---------------------------------------------------------------- error plumbing (thread-local)
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define P2M_CUDA_OK(expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      p2m::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +        \
+                     __FILE__ + ":" + std::to_string(__LINE__) + ")");                        \
+      return P2M_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define P2M_LAUNCH_OK()                                                                       \
+  do {                                                                                        \
+    p2m::count_launch();                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      p2m::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + " (" +  \
+                     __FILE__ + ":" + std::to_string(__LINE__) + ")");                        \
+      return P2M_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define P2M_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != P2M_OK) return _s; \
+  } while (0)
+
+// ---------------------------------------------------------------- device-resident hierarchy level
+// L~ of one level in CSR with RELATIVE column offsets: the neighbour of flat activation row
+// r = b*V + v is row r + reloff[p], so kernels never need (b, v) separately (block-diagonal I_B (x) L~).
+struct DevLevel {
+  int V = 0;
+  int nnz = 0;
+  int max_row_nnz = 0;
+  int* rowptr = nullptr;   // [V+1]
+  int* reloff = nullptr;   // [nnz] col - row
+  float* val = nullptr;    // [nnz]
+};
+
+// 2-tap channel resampling table (F.interpolate(mode='linear', align_corners=False) along channels,
+// meshnet.py:109,114) and its transpose for the backward pass.
+struct InterpTable {
+  int fin = 0, fout = 0;
+  int* i0 = nullptr;      // [fout]
+  int* i1 = nullptr;      // [fout]
+  float* lam = nullptr;   // [fout]  out[j] = (1-lam)*x[i0] + lam*x[i1]
+  int* t_ptr = nullptr;   // [fin+1]   transpose CSR: dx[i] = sum_p t_w[p] * dout[t_idx[p]]
+  int* t_idx = nullptr;
+  float* t_w = nullptr;
+};
+
+// ---------------------------------------------------------------- SIMT kernels (kernels_simt.cu)
+// Chebyshev basis T = [T0 | T1 | T2] (each F wide, row stride 3F) of x.  x is [rows_phys, F]; when
+// in_unpool, logical row r reads physical row r>>1 (nearest x2 unpool, meshnet.py:71-78).
+int launch_cheb_basis(const DevLevel& g, const float* x, int in_unpool, int rows, int F, float* T, cudaStream_t s);
+
+struct Epilogue {
+  const float* bias = nullptr;    // [N] added first
+  const float* scale = nullptr;   // [N] then v = v*scale + shift
+  const float* shift = nullptr;
+  int relu = 0;
+  const float* res = nullptr;     // residual source [rows(/2), res_F], channel-resampled to N, added last
+  int res_F = 0;
+  int res_unpool = 0;
+  const int* res_i0 = nullptr;
+  const int* res_i1 = nullptr;
+  const float* res_lam = nullptr;
+};
+// C[M,N] = A[M,K] * op(B) (+ epilogue); b_is_kn: B stored [K,N] row-major, else [N,K] row-major.
+int launch_gemm(const float* A, int lda, const float* B, int ldb, int b_is_kn, float* C, int ldc, int M, int N, int K,
+                const Epilogue& ep, cudaStream_t s);
+// C[N1,N2] (+)= A[M,N1]^T * B[M,N2]  (C must be zeroed by the caller; split over M with atomics)
+int launch_gemm_tn_atomic(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N1, int N2,
+                          cudaStream_t s);
+
+int launch_permute_w(const float* W, float* Wp, int fout, int fin, cudaStream_t s);      // [n,f*3+k] -> [n,k*fin+f]
+int launch_unpermute_w(const float* Wp, float* W, int fout, int fin, cudaStream_t s);    // inverse
+int launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
+
+// BatchNorm1d over rows (cheby_graph_conv.py:38-39; meshnet.py:55): eps 1e-5, momentum 0.1
+int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv, const float* bias,
+                        float* scale, float* shift, int F, cudaStream_t s);
+int launch_col_stats(const float* z, int rows, int F, double* sums /*[2F] zeroed here*/, cudaStream_t s);
+int launch_bn_finalize(const double* sums, int rows, int F, const float* gamma, const float* beta, float* rm, float* rv,
+                       int64_t* nbt, float* save_mean, float* save_invstd, float* scale, float* shift, cudaStream_t s);
+// a = relu?(z*scale+shift) (+ resampled residual)
+int launch_affine_act(const float* z, int rows, int F, const float* scale, const float* shift, int relu,
+                      const float* res, int res_F, int res_unpool, const InterpTable* it, float* a, cudaStream_t s);
+// BN+ReLU backward: g_a (grad wrt a = relu(bn(z)) [+ residual]) -> g_z (in place allowed); dgamma, dbeta
+// written.  The ReLU mask is recomputed from z (block-end activations already include the residual).
+int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* beta,
+                       const float* mean, const float* invstd, int relu, double* sums /*[2F] scratch*/, float* dgamma,
+                       float* dbeta, float* g_z, cudaStream_t s);
+int launch_col_sum(const float* g, int rows, int F, double* scratch /*[F]*/, float* out, cudaStream_t s);
+
+// dX of the Chebyshev basis: given dT [rows,3F] (blocks dT0|dT1|dT2):
+//   dXl = dT0 - dT2 + L~ (dT1 + 2 L~ dT2)   (L~ symmetric)   [+ resample^T(g_res)]
+// written to dx; when out_pairsum, dx has rows/2 rows and dx[p] = dXl[2p] + dXl[2p+1].
+int launch_cheb_basis_bwd(const DevLevel& g, const float* dT, int rows, int F, float* U /*[rows,F] scratch*/,
+                          const float* g_res, int res_Fout, const InterpTable* it, int out_pairsum, float* dx,
+                          cudaStream_t s);
+
+// ---------------------------------------------------------------- tcgen05 path (cheb_umma.cu)
+struct UmmaConvArgs {
+  const DevLevel* g;
+  const float* x;           // [rows(/2), Fin]
+  int in_unpool;
+  int rows;                 // B*V logical rows
+  int fin, fout;
+  const void* wpack;        // packed fp16 hi/lo weights from launch_umma_pack_weights
+  Epilogue ep;
+  float* y;                 // [rows, fout]
+  double* stats;            // optional [2*fout] column sum / sumsq of the pre-activation output (train)
+};
+bool umma_conv_supported(int V, int fin, int fout);
+size_t umma_wpack_bytes(int fin, int fout);
+int launch_umma_pack_weights(const float* W /*[fout, fin*3] ref layout*/, int fin, int fout, void* wpack, cudaStream_t s);
+int launch_umma_conv(const UmmaConvArgs& a, int sm_count, cudaStream_t s);
+
+}  // namespace p2m
