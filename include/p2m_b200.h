@@ -80,6 +80,9 @@ int p2m_model_num_layers(const p2m_model_t* m);
 /* layer geometry: out[0]=level index, [1]=V, [2]=Fin, [3]=Fout, [4]=has_bn, [5]=relu */
 int p2m_model_layer_info(const p2m_model_t* m, int layer, int32_t out[6]);
 int p2m_model_set_precision(p2m_model_t* m, int precision);
+/* Debug: device-synchronises and returns the status word of the tcgen05 kernels (0 = no mbarrier
+ * wait ever timed out; otherwise the id of the wait that did).                                      */
+int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out);
 
 /* Bytes of device workspace p2m_meshnet_forward needs for batch B.  In training mode the workspace
  * also carries what p2m_meshnet_backward reads, so it must stay alive and untouched in between.   */

@@ -19,6 +19,15 @@ import torch
 from . import _lib
 
 _graph_cache = {}
+_default_precision = _lib.P2M_PREC_FP32_SIMT
+
+
+def set_default_precision(precision: str):
+    """'fp32' (CUDA cores) or 'fp16x3' (tcgen05 tensor cores) for graph_conv_cheby calls."""
+    global _default_precision
+    _default_precision = {"fp32": _lib.P2M_PREC_FP32_SIMT, "fp16x3": _lib.P2M_PREC_FP16X3_TC}[precision]
+    for _, gh in list(_graph_cache.values()):
+        gh.apply_precision()
 
 
 class GraphHandle:
@@ -49,8 +58,18 @@ class GraphHandle:
             out = C.c_void_p()
             _lib.check(lib.p2m_model_create(C.byref(desc), C.byref(out)), "p2m_model_create")
             h = out.value
+            _lib.check(lib.p2m_model_set_precision(h, _default_precision), "p2m_model_set_precision")
             self._handles[device_index] = h
         return h
+
+    def apply_precision(self):
+        for h in self._handles.values():
+            _lib.check(_lib.load().p2m_model_set_precision(h, _default_precision), "p2m_model_set_precision")
+
+    def kernel_status(self, device_index: int) -> int:
+        out = C.c_int32(0)
+        _lib.check(_lib.load().p2m_debug_kernel_status(self.handle(device_index), C.byref(out)), "kernel_status")
+        return out.value
 
     def __del__(self):
         try:

@@ -189,32 +189,6 @@ int launch_cheb_basis_bwd(const DevLevel& g, const float* dT, int rows, int F, f
 // =====================================================================================
 // Generic fp32 GEMM  C = A * op(B)  with the conv epilogue
 // =====================================================================================
-struct EpiDev {
-  const float* bias;
-  const float* scale;
-  const float* shift;
-  int relu;
-  const float* res;
-  int res_F;
-  int res_unpool;
-  const int* i0;
-  const int* i1;
-  const float* lam;
-};
-
-__device__ __forceinline__ float apply_epilogue(float v, long long r, int n, const EpiDev& ep) {
-  if (ep.bias) v += ep.bias[n];
-  if (ep.scale) v = fmaf(v, ep.scale[n], ep.shift[n]);
-  if (ep.relu) v = fmaxf(v, 0.f);
-  if (ep.res) {
-    long long pr = ep.res_unpool ? (r >> 1) : r;
-    const float* rr = ep.res + pr * ep.res_F;
-    float l = ep.lam[n];
-    v += (1.f - l) * rr[ep.i0[n]] + l * rr[ep.i1[n]];
-  }
-  return v;
-}
-
 template <int BM, int BN, int BK, bool B_KN>
 __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                               float* __restrict__ C, int ldc, int M, int N, int K, EpiDev ep) {
@@ -291,7 +265,7 @@ int launch_gemm(const float* A, int lda, const float* B, int ldb, int b_is_kn, f
     set_error("gemm: empty problem");
     return P2M_ERR_INVALID;
   }
-  EpiDev ep{e.bias, e.scale, e.shift, e.relu, e.res, e.res_F, e.res_unpool, e.res_i0, e.res_i1, e.res_lam};
+  EpiDev ep = to_dev(e);
   if (N > 64) {
     dim3 grid(cdiv(M, 128), cdiv(N, 128));
     if (b_is_kn)
@@ -510,8 +484,8 @@ int launch_affine_act(const float* z, int rows, int F, const float* scale, const
 
 // BN + ReLU backward.  Pass 1: s1 = sum g', s2 = sum g' * zhat  with g' = g_a * [bn(z) > 0].
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ z, const float* __restrict__ g_a,
-                                                       long long rows, int F, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                                       long long rows, int F, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, int relu,
                                                        double* __restrict__ sums) {
   extern __shared__ float sm[];
@@ -523,11 +497,12 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
   for (int f = fl; f < F; f += lanes) {
     float s = 0.f, q = 0.f;
     if (rr < rl) {
-      float mu = mean[f], is = invstd[f], ga = gamma[f], be = beta[f];
+      float mu = mean[f], is = invstd[f], sc = scale[f], sh = shift[f];
       for (long long r = rbeg + rr; r < rend; r += rl) {
-        float zh = (z[r * F + f] - mu) * is;
+        float zv = z[r * F + f];
+        float zh = (zv - mu) * is;
         float g = g_a[r * F + f];
-        if (relu && !(fmaf(zh, ga, be) > 0.f)) g = 0.f;
+        if (relu && !(fmaf(zv, sc, sh) > 0.f)) g = 0.f;  // exactly the forward's activation test
         s += g;
         q = fmaf(g, zh, q);
       }
@@ -548,7 +523,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
 }
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ z, const float* __restrict__ g_a,
                                                       long long rows, int F, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, const float* __restrict__ mean,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      const float* __restrict__ mean,
                                                       const float* __restrict__ invstd, int relu,
                                                       const double* __restrict__ sums, float* __restrict__ dgamma,
                                                       float* __restrict__ dbeta, float* __restrict__ g_z) {
@@ -559,22 +535,23 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
   }
   if (idx >= rows * F) return;
   int f = (int)(idx % F);
-  float zh = (z[idx] - mean[f]) * invstd[f];
+  float zv = z[idx];
+  float zh = (zv - mean[f]) * invstd[f];
   float g = g_a[idx];
-  if (relu && !(fmaf(zh, gamma[f], beta[f]) > 0.f)) g = 0.f;
+  if (relu && !(fmaf(zv, scale[f], shift[f]) > 0.f)) g = 0.f;
   float m1 = (float)(sums[f] / (double)rows);
   float m2 = (float)(sums[F + f] / (double)rows);
   g_z[idx] = gamma[f] * invstd[f] * (g - m1 - zh * m2);
 }
-int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* beta,
-                        const float* mean, const float* invstd, int relu, double* sums, float* dgamma, float* dbeta,
-                        float* g_z, cudaStream_t s) {
+int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu, double* sums,
+                       float* dgamma, float* dbeta, float* g_z, cudaStream_t s) {
   P2M_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
-  k_bn_bwd_reduce<<<cdiv(rows, STAT_ROWS), 256, 2 * 256 * sizeof(float), s>>>(z, g_a, rows, F, gamma, beta, mean,
+  k_bn_bwd_reduce<<<cdiv(rows, STAT_ROWS), 256, 2 * 256 * sizeof(float), s>>>(z, g_a, rows, F, scale, shift, mean,
                                                                                invstd, relu, sums);
   P2M_LAUNCH_OK();
-  k_bn_bwd_apply<<<cdiv((long long)rows * F, 256), 256, 0, s>>>(z, g_a, rows, F, gamma, beta, mean, invstd, relu, sums,
-                                                               dgamma, dbeta, g_z);
+  k_bn_bwd_apply<<<cdiv((long long)rows * F, 256), 256, 0, s>>>(z, g_a, rows, F, gamma, scale, shift, mean, invstd, relu,
+                                                               sums, dgamma, dbeta, g_z);
   P2M_LAUNCH_OK();
   return P2M_OK;
 }

@@ -47,6 +47,7 @@ struct p2m_model {
   std::vector<Block> blocks;
   int n_joint = 0, cin = 0, cout = 0;
   int fc_in = 0, fc_out = 0;
+  int* kernel_status = nullptr;  // device word set by a tcgen05 kernel whose mbarrier wait timed out
   std::vector<void*> owned;  // device allocations to free
 };
 
@@ -124,6 +125,7 @@ struct Sizes {
   size_t max_T = 0;      // floats: max rows*3*fin
   size_t max_U = 0;      // floats: max rows*fin
   size_t max_w = 0;      // floats: max fout*3*fin
+  size_t max_wpack = 0;  // bytes: packed fp16 hi/lo weight image of the tcgen05 path
   int max_f = 0;
 };
 
@@ -136,6 +138,8 @@ Sizes model_sizes(const p2m_model* m, int B) {
     s.max_T = std::max(s.max_T, rows * 3 * L.fin);
     s.max_U = std::max(s.max_U, rows * L.fin);
     s.max_w = std::max(s.max_w, (size_t)L.fout * 3 * L.fin);
+    if (umma_conv_supported(m->levels[L.level], L.fin, L.fout))
+      s.max_wpack = std::max(s.max_wpack, umma_wpack_bytes(L.fin, L.fout));
     s.max_f = std::max(s.max_f, std::max(L.fin, L.fout));
   }
   s.max_act = std::max(s.max_act, (size_t)B * m->fc_out);
@@ -147,6 +151,7 @@ Sizes model_sizes(const p2m_model* m, int B) {
 struct WsMap {
   float* T;
   float* wp_scratch;
+  unsigned char* wpack;   // tcgen05 packed weights (one layer at a time)
   float* scale_scratch;   // [2*max_f] eval folded scale/shift
   double* sums;           // [2*max_f]
   float* rot[3];          // eval: rotating activation buffers
@@ -162,6 +167,7 @@ WsMap map_workspace(const p2m_model* m, int B, int training, void* base) {
   Bump b(base);
   w.T = b.take<float>(s.max_T);
   w.wp_scratch = b.take<float>(s.max_w);
+  w.wpack = b.take<unsigned char>(std::max(s.max_wpack, (size_t)16));
   w.scale_scratch = b.take<float>(2 * (size_t)s.max_f);
   w.sums = b.take<double>(2 * (size_t)s.max_f);
   const size_t nl = m->layers.size();
@@ -215,10 +221,24 @@ BwdMap map_scratch(const p2m_model* m, int B, void* base) {
 // ---- one conv layer, linear part + epilogue -------------------------------------------------
 // y = epilogue( [T0|T1|T2](x) * Wp^T )
 int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpool, const float* w_ref, float* T,
-                float* wp, const Epilogue& ep, float* y, cudaStream_t s) {
+                float* wp, unsigned char* wpack, const Epilogue& ep, float* y, cudaStream_t s) {
   const int rows = B * L.V;
   const DevLevel& g = m->levels[L.level];
-  P2M_TRY(launch_permute_w(w_ref, wp, L.fout, L.fin, s));
+  P2M_TRY(launch_permute_w(w_ref, wp, L.fout, L.fin, s));  // k-major copy, also what backward's dT GEMM reads
+  if (m->precision == P2M_PREC_FP16X3_TC && wpack != nullptr && umma_conv_supported(g, L.fin, L.fout)) {
+    P2M_TRY(launch_umma_pack_weights(w_ref, L.fin, L.fout, wpack, s));
+    UmmaConvArgs a;
+    a.g = &g;
+    a.x = x;
+    a.in_unpool = in_unpool;
+    a.batch = B;
+    a.fin = L.fin;
+    a.fout = L.fout;
+    a.wpack = wpack;
+    a.ep = ep;
+    a.y = y;
+    return launch_umma_conv(a, m->kernel_status, s);
+  }
   P2M_TRY(launch_cheb_basis(g, x, in_unpool, rows, L.fin, T, s));
   P2M_TRY(launch_gemm(T, 3 * L.fin, wp, 3 * L.fin, 0, y, L.fout, rows, L.fout, 3 * L.fin, ep, s));
   return P2M_OK;
@@ -302,11 +322,20 @@ int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
       }
     }
     int st;
-    if ((st = upload(m, rowptr, &g.rowptr)) || (st = upload(m, rel, &g.reloff)) || (st = upload(m, val, &g.val))) {
+    if ((st = upload(m, rowptr, &g.rowptr)) || (st = upload(m, rel, &g.reloff)) || (st = upload(m, val, &g.val)) ||
+        (st = build_umma_level_meta(rp, d->colidx[l], d->values[l], g.V, &g, &m->owned))) {
       p2m_model_destroy(m);
       return st;
     }
     m->levels.push_back(g);
+  }
+  {
+    std::vector<int> zero(1, 0);
+    int st = upload(m, zero, &m->kernel_status);
+    if (st) {
+      p2m_model_destroy(m);
+      return st;
+    }
   }
   // ---- plan (meshnet.py:21-33, 86-94)
   const int nb = d->n_blocks;
@@ -400,6 +429,19 @@ int p2m_model_layer_info(const p2m_model_t* m, int layer, int32_t out[6]) {
   return P2M_OK;
 }
 
+int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out) {
+  if (!m || !out) {
+    set_error("debug_kernel_status: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  P2M_CUDA_OK(cudaSetDevice(m->device));
+  P2M_CUDA_OK(cudaDeviceSynchronize());
+  int v = 0;
+  P2M_CUDA_OK(cudaMemcpy(&v, m->kernel_status, sizeof(int), cudaMemcpyDeviceToHost));
+  *out = v;
+  return P2M_OK;
+}
+
 int p2m_model_set_precision(p2m_model_t* m, int precision) {
   if (!m || (precision != P2M_PREC_FP32_SIMT && precision != P2M_PREC_FP16X3_TC)) {
     set_error("set_precision: bad argument");
@@ -486,7 +528,7 @@ int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, f
             }
           out = w.rot[out_buf];
         }
-        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, ep, out, s));
+        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s));
         cur = out;
         cur_buf = out_buf;
         cur_unpool = 0;
@@ -494,7 +536,7 @@ int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, f
         Epilogue ep;
         ep.bias = P->cl_b[li];
         float* z = last ? y : w.z[li];
-        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp[li], ep, z, s));
+        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp[li], w.wpack, ep, z, s));
         if (L.bn) {
           P2M_TRY(launch_col_stats(z, rows, L.fout, w.sums, s));
           P2M_TRY(launch_bn_finalize(w.sums, rows, L.fout, P->bn_w[li], P->bn_b[li], P->bn_rm[li], P->bn_rv[li],
@@ -611,8 +653,8 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params
       }
       if (L.bn) {
         int tgt = (g_cur_buf >= 0 && g_cur_buf != keep_buf) ? g_cur_buf : free_buf(g_cur_buf, keep_buf, -1);
-        P2M_TRY(launch_bn_relu_bwd(w.z[li], g_cur, rows, L.fout, P->bn_w[li], P->bn_b[li], w.mean[li], w.invstd[li],
-                                   L.relu, sc.sums, G->bn_w[li], G->bn_b[li], sc.G[tgt], s));
+        P2M_TRY(launch_bn_relu_bwd(w.z[li], g_cur, rows, L.fout, P->bn_w[li], w.scale[li], w.shift[li], w.mean[li],
+                                   w.invstd[li], L.relu, sc.sums, G->bn_w[li], G->bn_b[li], sc.G[tgt], s));
         g_z = sc.G[tgt];
         gz_buf = tgt;
       }
@@ -666,7 +708,8 @@ size_t p2m_cheb_conv_workspace_bytes(const p2m_model_t* m, int level, int batch,
   if (!m || level < 0 || level >= (int)m->levels.size()) return 0;
   size_t rows = (size_t)batch * m->levels[level].V;
   return align_up(rows * 3 * fin * 4) + align_up((size_t)fout * 3 * fin * 4) * 2 + align_up(rows * fin * 4) +
-         align_up(rows * fout * 4) + align_up(2 * (size_t)std::max(fin, fout) * 8) + align_up(2 * (size_t)fout * 4) + ALIGN;
+         align_up(rows * fout * 4) + align_up(2 * (size_t)std::max(fin, fout) * 8) + align_up(2 * (size_t)fout * 4) +
+         align_up(umma_wpack_bytes(((fin + 31) / 32) * 32, fout) + 16) + ALIGN;
 }
 
 int p2m_cheb_conv_fwd(p2m_model_t* m, const p2m_conv_fwd_args_t* a, void* workspace, size_t workspace_bytes,
@@ -694,11 +737,12 @@ int p2m_cheb_conv_fwd(p2m_model_t* m, const p2m_conv_fwd_args_t* a, void* worksp
   float* z = b.take<float>(rows * L.fout);
   double* sums = b.take<double>(2 * (size_t)std::max(L.fin, L.fout));
   float* sc = b.take<float>(2 * (size_t)L.fout);
+  unsigned char* wpack = b.take<unsigned char>(umma_wpack_bytes(((L.fin + 31) / 32) * 32, L.fout) + 16);
   Epilogue ep;
   if (a->bn_mode == 0) {
     ep.bias = a->bias;
     ep.relu = a->relu;
-    return conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, ep, a->y, s);
+    return conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, wpack, ep, a->y, s);
   }
   if (!a->bn_weight || !a->bn_bias) {
     set_error("cheb_conv_fwd: BatchNorm parameters missing");
@@ -714,10 +758,10 @@ int p2m_cheb_conv_fwd(p2m_model_t* m, const p2m_conv_fwd_args_t* a, void* worksp
     ep.scale = sc;
     ep.shift = sc + L.fout;
     ep.relu = a->relu;
-    return conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, ep, a->y, s);
+    return conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, wpack, ep, a->y, s);
   }
   ep.bias = a->bias;
-  P2M_TRY(conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, ep, z, s));
+  P2M_TRY(conv_linear(m, L, a->batch, a->x, 0, a->weight, T, wp, wpack, ep, z, s));
   P2M_TRY(launch_col_stats(z, (int)rows, L.fout, sums, s));
   P2M_TRY(launch_bn_finalize(sums, (int)rows, L.fout, a->bn_weight, a->bn_bias, a->bn_running_mean, a->bn_running_var,
                              a->bn_num_batches_tracked, a->save_mean, a->save_invstd, sc, sc + L.fout, s));

@@ -51,6 +51,12 @@ struct DevLevel {
   int* rowptr = nullptr;   // [V+1]
   int* reloff = nullptr;   // [nnz] col - row
   float* val = nullptr;    // [nnz]
+  // tcgen05 path: per-tile-pattern halo / local-CSR blobs (cheb_umma.cu)
+  int n_pattern = 0;                    // tiles per mesh = ceil(V / 128)
+  const unsigned char* tile_meta = nullptr;   // [n_pattern][meta_stride]
+  const int* tile_meta_bytes = nullptr;       // [n_pattern] bytes to copy (multiple of 16)
+  int meta_stride = 0;
+  int max_h1 = 0, max_h2 = 0;
 };
 
 // 2-tap channel resampling table (F.interpolate(mode='linear', align_corners=False) along channels,
@@ -82,6 +88,37 @@ struct Epilogue {
   const int* res_i1 = nullptr;
   const float* res_lam = nullptr;
 };
+#ifdef __CUDACC__
+// Device-side view of Epilogue + the per-element epilogue shared by the SIMT GEMM and the tcgen05 conv.
+struct EpiDev {
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int relu;
+  const float* res;
+  int res_F;
+  int res_unpool;
+  const int* i0;
+  const int* i1;
+  const float* lam;
+};
+inline EpiDev to_dev(const Epilogue& e) {
+  return EpiDev{e.bias, e.scale, e.shift, e.relu, e.res, e.res_F, e.res_unpool, e.res_i0, e.res_i1, e.res_lam};
+}
+__device__ __forceinline__ float apply_epilogue(float v, long long r, int n, const EpiDev& ep) {
+  if (ep.bias) v += ep.bias[n];
+  if (ep.scale) v = fmaf(v, ep.scale[n], ep.shift[n]);
+  if (ep.relu) v = fmaxf(v, 0.f);
+  if (ep.res) {
+    long long pr = ep.res_unpool ? (r >> 1) : r;
+    const float* rr = ep.res + pr * ep.res_F;
+    float l = ep.lam[n];
+    v += (1.f - l) * rr[ep.i0[n]] + l * rr[ep.i1[n]];
+  }
+  return v;
+}
+#endif
+
 // C[M,N] = A[M,K] * op(B) (+ epilogue); b_is_kn: B stored [K,N] row-major, else [N,K] row-major.
 int launch_gemm(const float* A, int lda, const float* B, int ldb, int b_is_kn, float* C, int ldc, int M, int N, int K,
                 const Epilogue& ep, cudaStream_t s);
@@ -104,9 +141,9 @@ int launch_affine_act(const float* z, int rows, int F, const float* scale, const
                       const float* res, int res_F, int res_unpool, const InterpTable* it, float* a, cudaStream_t s);
 // BN+ReLU backward: g_a (grad wrt a = relu(bn(z)) [+ residual]) -> g_z (in place allowed); dgamma, dbeta
 // written.  The ReLU mask is recomputed from z (block-end activations already include the residual).
-int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* beta,
-                       const float* mean, const float* invstd, int relu, double* sums /*[2F] scratch*/, float* dgamma,
-                       float* dbeta, float* g_z, cudaStream_t s);
+int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu,
+                       double* sums /*[2F] scratch*/, float* dgamma, float* dbeta, float* g_z, cudaStream_t s);
 int launch_col_sum(const float* g, int rows, int F, double* scratch /*[F]*/, float* out, cudaStream_t s);
 
 // dX of the Chebyshev basis: given dT [rows,3F] (blocks dT0|dT1|dT2):
@@ -121,16 +158,18 @@ struct UmmaConvArgs {
   const DevLevel* g;
   const float* x;           // [rows(/2), Fin]
   int in_unpool;
-  int rows;                 // B*V logical rows
+  int batch;                // rows = batch * g->V
   int fin, fout;
   const void* wpack;        // packed fp16 hi/lo weights from launch_umma_pack_weights
   Epilogue ep;
   float* y;                 // [rows, fout]
-  double* stats;            // optional [2*fout] column sum / sumsq of the pre-activation output (train)
 };
-bool umma_conv_supported(int V, int fin, int fout);
+// Host: build the per-tile halo metadata of one level (uploads; device pointers appended to `owned`).
+int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
+                          std::vector<void*>* owned);
+bool umma_conv_supported(const DevLevel& g, int fin, int fout);
 size_t umma_wpack_bytes(int fin, int fout);
 int launch_umma_pack_weights(const float* W /*[fout, fin*3] ref layout*/, int fin, int fout, void* wpack, cudaStream_t s);
-int launch_umma_conv(const UmmaConvArgs& a, int sm_count, cudaStream_t s);
+int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, cudaStream_t s);
 
 }  // namespace p2m

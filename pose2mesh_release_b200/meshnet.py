@@ -94,6 +94,12 @@ class BakedHierarchy:
             for h in self._handles.values():
                 _lib.check(_lib.load().p2m_model_set_precision(h, precision), "p2m_model_set_precision")
 
+    def kernel_status(self, device_index: int) -> int:
+        """0 unless a tcgen05 kernel's bounded mbarrier wait timed out (debug aid; synchronises)."""
+        out = C.c_int32(0)
+        _lib.check(_lib.load().p2m_debug_kernel_status(self.handle(device_index), C.byref(out)), "kernel_status")
+        return out.value
+
     def __deepcopy__(self, memo):  # handles are per-process device state: share, never copy
         return self
 
@@ -156,7 +162,6 @@ class _MeshNetFunction(torch.autograd.Function):
             ctx.hier, ctx.n_layers, ctx.ws, ctx.ws_bytes = hier, n_layers, ws, ws_bytes
             ctx.save_for_backward(x, *params)
         ctx.differentiable = needs_grad
-        ctx.mark_non_differentiable(*[])
         return y
 
     @staticmethod
@@ -262,7 +267,7 @@ class Pose2Mesh(nn.Module):
         bn_b = [m.bias for m in self.bn if m is not None]
         return n, [self.fc.weight, self.fc.bias, *cl_w, *cl_b, *bn_w, *bn_b]
 
-    def _buffers(self):
+    def _bn_buffers(self):
         rm = [None if m is None else m.running_mean for m in self.bn]
         rv = [None if m is None else m.running_var for m in self.bn]
         nbt = [None if m is None else m.num_batches_tracked for m in self.bn]
@@ -279,7 +284,7 @@ class Pose2Mesh(nn.Module):
         for p in params:
             if p.device != x.device:
                 raise RuntimeError("parameters and input live on different devices")
-        return _MeshNetFunction.apply(x, self._hier, self.training, self._buffers(), n, *params)
+        return _MeshNetFunction.apply(x, self._hier, self.training, self._bn_buffers(), n, *params)
 
     def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
         """Inference with HOST tensors through p2m_meshnet_forward_host: H2D of the poses, the eval
@@ -300,7 +305,7 @@ class Pose2Mesh(nn.Module):
             self._host_ws = ws
         n, params = self._flat_params()
         n_bn = n - 1
-        rm, rv, nbt = self._buffers()
+        rm, rv, nbt = self._bn_buffers()
         table = _param_table(params[0], params[1], params[2:2 + n], params[2 + n:2 + 2 * n],
                              list(params[2 + 2 * n:2 + 2 * n + n_bn]) + [None],
                              list(params[2 + 2 * n + n_bn:]) + [None], rm, rv, nbt)

@@ -236,3 +236,48 @@ def test_edge_cases():
     y = model(x)
     with pytest.raises(RuntimeError, match="eval-mode"):
         y.sum().backward()
+
+
+UMMA_SHAPES = [
+    # (fixture, level index in the fixture's list, B, Fin, Fout)
+    ("smpl_small", 0, 2, 128, 128),   # V=2048: 16 full tiles
+    ("smpl_small", 0, 1, 64, 64),
+    ("smpl_small", 1, 3, 256, 256),   # V=1024, N=256 ring of 2
+    ("smpl_small", 2, 2, 256, 128),   # V=512
+    ("smpl_small", 3, 2, 64, 128),    # V=256
+    ("smpl_small", 5, 5, 32, 64),     # V=64 < tile
+    ("mano_like", 0, 2, 128, 128),    # V=1088 = 8.5 tiles: ragged last tile
+    ("mano_like", 1, 2, 256, 256),    # V=544
+    ("mano_like", 3, 3, 128, 256),    # V=136
+]
+
+
+@pytest.mark.parametrize("case", UMMA_SHAPES, ids=lambda c: f"{c[0]}-L{c[1]}-B{c[2]}-{c[3]}to{c[4]}")
+def test_tcgen05_conv_matches_oracle(case):
+    """The fused tcgen05 kernel (SpMM producers + fp16x3 UMMA + epilogue) on one layer, against the
+    CPU oracle, incl. ragged tiles (V % 128 != 0), V < 128 and every (Fin, Fout) class."""
+    from oracle import meshnet_oracle as mo
+    from pose2mesh_release_b200 import cheby_graph_conv as cgc
+
+    name, level, b, fin, fout = case
+    mats, _ = graph_from_fixture(name)
+    L = mats[level]
+    lap = mo.laplacians_to_torch([L], drop_second_coarsest=False)[0]
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(b, L.shape[0], fin, generator=g)
+    w = (torch.rand(fout, 3 * fin, generator=g) * 2 - 1) * float(np.sqrt(2.0 / (3 * fin + fout)))
+    bias = torch.randn(fout, generator=g) * 0.1
+    cl = torch.nn.Linear(3 * fin, fout).to(dev())
+    cl.weight.data.copy_(w)
+    cl.bias.data.copy_(bias)
+    cgc.set_default_precision("fp16x3")
+    try:
+        gh = cgc.graph_handle(L)
+        with torch.no_grad():
+            y = cgc.graph_conv_cheby(x.to(dev()), cl, None, L, fout, 3)
+        assert gh.kernel_status(0) == 0, "a tcgen05 kernel timed out on an mbarrier"
+    finally:
+        cgc.set_default_precision("fp32")
+    yo = mo.cheb_conv(x, lap, w, bias)
+    err = rel_err(y, yo)
+    assert err < 2e-6, err
