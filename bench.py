@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — MeshNet hot-path benchmark (BASELINE.json metric: SMPL meshes/sec at B=256 per B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fwd|train] [--batch 256] [--precision fp16x3|fp32]
+    python bench.py --impl reference ...     # the reference algorithm on the host cores (oracle port)
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): batch 256 synthetic H36M 17-joint poses [256,17,5] ~ N(0,1),
+full coarse-to-fine MeshNet forward (eval mode, randomised BatchNorm running stats, random-init
+weights under torch.manual_seed(123)) on a synthetic 6890-vertex genus-0 mesh whose hierarchy has the
+real SMPL level sizes 12288/6144/.../96 (mesh seed 2; SMPL's topology is licence-gated).
+One "step" = one forward over one batch of 256 poses per GPU; N GPUs = N independent shards of a
+256*N batch (weak scaling, no data-path collective).  `--mode train` times forward+backward with an
+L1 loss to random targets plus the single NCCL all-reduce of the flat gradient (configs[2]/[4]).
+
+Printed JSON (one line, rank 0): see the task contract — `value` is device-timed whole-job meshes/s
+with inputs resident in HBM; `e2e` is the same metric through the C-ABI host entry point
+(p2m_meshnet_forward_host: pinned host poses in, host meshes out, copies inside the timed region);
+`roofline` describes the dominant kernel (the V=12288, 128->128 Chebyshev conv) from CUDA-event
+timings taken live; `cpu_baseline` is the CPU oracle on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MESH = dict(n_vertex=6890, seed=2, levels=9)
+WORKLOAD = "configs[1]: B=256 H36M-17 poses -> full MeshNet forward (eval), SMPL-size hierarchy 12288..96"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fwd", choices=["fwd", "train"])
+    ap.add_argument("--batch", type=int, default=256, help="poses per GPU per step")
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=24, help="meshes in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem():
+    from pose2mesh_release_b200 import graph as pg
+
+    face = pg.synthetic_sphere_faces(MESH["n_vertex"], MESH["seed"])
+    _, graph_L, _, perm_rev = pg.build_coarse_graphs(face, 17, pg.H36M_SKELETON, pg.H36M_FLIP_PAIRS,
+                                                     levels=MESH["levels"])
+    return graph_L, perm_rev
+
+
+def randomize_bn_(sd, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(sd):
+        if not k.startswith("bn."):
+            continue
+        t = sd[k]
+        if k.endswith(".weight") or k.endswith(".running_var"):
+            t.copy_(torch.rand(t.shape, generator=g) + 0.5)
+        elif k.endswith(".bias") or k.endswith(".running_mean"):
+            t.copy_(torch.randn(t.shape, generator=g) * 0.1)
+    return sd
+
+
+def cpu_port_meshes_per_s(graph_L, sample, threads=None):
+    """The reference algorithm on the host cores: the CPU oracle (a port; /root/reference does not
+    exist on the GPU box).  Eval forward on `sample` meshes, 1 small warm-up + 1 timed pass."""
+    from oracle import meshnet_oracle as mo
+
+    if threads:
+        torch.set_num_threads(threads)
+    laps = mo.laplacians_to_torch(graph_L)
+    torch.manual_seed(123)
+    sd = mo.randomize_bn_(mo.init_state_dict(5, 3, [m.shape[0] for m in laps], False), seed=7)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(sample, 17, 5, generator=g)
+    with torch.no_grad():
+        mo.forward(sd, laps, x[:2], training=False)
+        t0 = time.perf_counter()
+        mo.forward(sd, laps, x, training=False)
+        dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on all host
+    threads; each step is a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    graph_L, _ = build_problem()
+    from oracle import meshnet_oracle as mo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    laps = mo.laplacians_to_torch(graph_L)
+    torch.manual_seed(123)
+    sd = mo.randomize_bn_(mo.init_state_dict(5, 3, [m.shape[0] for m in laps], False), seed=7)
+    sample = 8
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(sample, 17, 5, generator=g)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            mo.forward(sd, laps, x[:2], training=False)
+        steps = max(1, min(args.steps, 6))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mo.forward(sd, laps, x, training=False)
+        dt = time.perf_counter() - t0
+    v = sample * steps / dt
+    line = {"impl": "reference", "metric": "SMPL meshes/sec", "value": v, "unit": "meshes/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{sample} meshes per step (bounded sample of the 256-pose batch)"},
+            "cpu_baseline": {"value": v, "unit": "meshes/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} x {sample} meshes, eval forward, CPU oracle (torch CPU kernels)"},
+            "e2e": {"value": v, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    from pose2mesh_release_b200 import _lib
+    from pose2mesh_release_b200.meshnet import Pose2Mesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    graph_L, perm_rev = build_problem()
+    torch.manual_seed(123)
+    model = Pose2Mesh(5, 3, graph_L, joint_set="human36")
+    model.load_state_dict(randomize_bn_({k: v.clone() for k, v in model.state_dict().items()}))
+    model = model.to(dev).set_precision(args.precision)
+    B = args.batch
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.randn(B, 17, 5, generator=g).pin_memory()
+    x = x_host.to(dev)
+    hbm_gbs, bf16_tf, peak_src = measured_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_graph = None
+    if args.mode == "fwd":
+        model.eval()
+
+        def step():
+            with torch.no_grad():
+                return model(x)
+
+        launch = step
+        if not args.no_graph:
+            # replay the ~100-launch forward from a CUDA graph (the library only enqueues on the current stream)
+            try:
+                side = torch.cuda.Stream()
+                with torch.cuda.stream(side):
+                    step()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    y_static = step()
+                torch.cuda.synchronize()
+                step_graph, launch = graph, graph.replay
+            except Exception as e:  # keep the bench alive; say so in the JSON
+                sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); running eagerly\n")
+                torch.cuda.synchronize()
+                step_graph, launch = None, step
+    else:
+        from pose2mesh_release_b200.dist import DataParallelStep
+
+        model.train()
+        dp = DataParallelStep(model)
+        tgt = torch.randn(B, model.num_vertices, 3, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+
+        def launch():
+            dp.zero_grad()
+            loss = (model(x) - tgt).abs().mean()
+            loss.backward()
+            dp.reduce_gradients()
+            return loss
+
+    for _ in range(max(args.warmup, 3)):
+        launch()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lib.p2m_launch_count_reset()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()               # evict L2 between timed iterations (not timed)
+        evs[i][0].record()
+        launch()
+        evs[i][1].record()
+    barrier()
+    launches_eager = lib.p2m_launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = B * world * args.steps / (total_ms * 1e-3)
+
+    # kernel launches per step: counted by the library while the step was captured / run eagerly
+    if step_graph is not None:
+        lib.p2m_launch_count_reset()
+        with torch.no_grad():
+            model(x)
+        torch.cuda.synchronize()
+        per_step_launches = lib.p2m_launch_count()
+    else:
+        per_step_launches = launches_eager // max(args.steps, 1)
+
+    # ---- end-to-end through the C-ABI host entry point (pinned host in / host out), wall clock
+    e2e = None
+    if args.mode == "fwd":
+        model.eval()
+        y_host = torch.empty((B, model.num_vertices, 3), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            model.forward_host(x_host, out=y_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.forward_host(x_host, out=y_host)      # synchronises its stream before returning
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / float(tt.item()), "unit": "meshes/s",
+               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4)}
+    else:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            xs = x_host.to(dev, non_blocking=True)
+            dp.zero_grad()
+            loss = (model(xs) - tgt).abs().mean()
+            loss.backward()
+            dp.reduce_gradients()
+            loss_host = loss.item()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / float(tt.item()), "unit": "meshes/s",
+               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4}
+
+    # ---- roofline of the dominant kernel: per-layer CUDA events inside the eval forward
+    roofline, layers = None, None
+    if rank == 0:
+        model.eval()
+        hier = model._hier
+        hier.set_profiling(local, True)
+        info = hier.layer_info(local)
+        acc = np.zeros(len(info))
+        reps = 5
+        with torch.no_grad():
+            for _ in range(reps):
+                flush.zero_()
+                model(x)
+                acc += np.array(hier.layer_times_ms(local))
+        hier.set_profiling(local, False)
+        acc /= reps
+        layers = []
+        for li, (d, ms) in enumerate(zip(info, acc)):
+            byt = 4.0 * d["V"] * (d["fin"] + d["fout"]) * B
+            fl = (2.0 * d["V"] * 3 * d["fin"] * d["fout"]) * B
+            layers.append({"layer": li, "V": d["V"], "fin": d["fin"], "fout": d["fout"], "ms": round(float(ms), 4),
+                           "GBps": round(byt / ms * 1e-6, 1), "TFLOPs": round(fl / ms * 1e-9, 1)})
+        dom = [i for i, d in enumerate(info) if d["V"] == info[-1]["V"] and d["fin"] == 128 and d["fout"] == 128]
+        if dom:
+            ms = float(np.mean([acc[i] for i in dom]))
+            d = info[dom[0]]
+            byt = 4.0 * d["V"] * (d["fin"] + d["fout"]) * B          # 4*V*(Fin+Fout) per mesh
+            fl = (2.0 * d["V"] * 3 * d["fin"] * d["fout"] + 2.0 * (2 * 53616 * d["fin"]) + 2.0 * d["V"] * d["fin"]) * B
+            ach = byt / (ms * 1e-3) * 1e-9
+            roofline = {"bound": "hbm", "kernel": f"cheb conv V={d['V']} {d['fin']}->{d['fout']} K=3 (layers {dom})",
+                        "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": None,
+                        "ms_per_launch": ms, "algorithmic_bytes": byt, "algorithmic_flops": fl,
+                        "tensor_TFLOPs": fl / (ms * 1e-3) * 1e-12, "tensor_frac_of_bf16_peak": fl / (ms * 1e-3) * 1e-12 / bf16_tf,
+                        "peak_source": peak_src,
+                        "note": "layer time includes the weight pack/permute launches (<1%); precision " + args.precision}
+
+    cpu_baseline = None
+    if rank == 0 and args.cpu_sample > 0 and args.mode == "fwd":
+        cores = os.cpu_count() or 1
+        v, dt = cpu_port_meshes_per_s(graph_L, args.cpu_sample, cores)
+        cpu_baseline = {"value": v, "unit": "meshes/s", "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_sample} meshes, eval forward, CPU oracle (torch CPU kernels), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "SMPL meshes/sec" if args.mode == "fwd" else "SMPL meshes/sec (fwd+bwd train step)",
+            "value": value, "unit": "meshes/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tcgen05 fp16x3 split, fp32 accumulate)" if args.precision == "fp16x3" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.mode == "fwd" else
+                       "configs[2]/[4]: B=256/GPU fwd+bwd, L1 loss, train-mode BatchNorm, one NCCL all-reduce of the flat gradient",
+                       "batch_per_gpu": B, "global_batch": B * world, "mesh": "synthetic genus-0, 6890 verts, seed 2",
+                       "levels": [int(m.shape[0]) for m in graph_L], "precision": args.precision,
+                       "parallelism": f"dp{world} (independent shards, no data-path collective)" if args.mode == "fwd"
+                       else f"dp{world} (single all-reduce per step)",
+                       "l2": "256 MiB buffer written between timed iterations (outside the event pairs)",
+                       "cuda_graph": step_graph is not None},
+            "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "gpu_launches_per_step": int(per_step_launches),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "layers": layers,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

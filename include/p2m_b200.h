@@ -80,6 +80,10 @@ int p2m_model_num_layers(const p2m_model_t* m);
 /* layer geometry: out[0]=level index, [1]=V, [2]=Fin, [3]=Fout, [4]=has_bn, [5]=relu */
 int p2m_model_layer_info(const p2m_model_t* m, int layer, int32_t out[6]);
 int p2m_model_set_precision(p2m_model_t* m, int precision);
+/* Profiling: when enabled, the eval forward records a CUDA event pair (on the caller's stream) around
+ * every conv layer; p2m_model_layer_times_ms returns the last forward's per-layer device times.      */
+int p2m_model_set_profiling(p2m_model_t* m, int enable);
+int p2m_model_layer_times_ms(p2m_model_t* m, float* out_ms, int n);
 /* Debug: device-synchronises and returns the status word of the tcgen05 kernels (0 = no mbarrier
  * wait ever timed out; otherwise the id of the wait that did).                                      */
 int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out);

@@ -48,6 +48,8 @@ struct p2m_model {
   int n_joint = 0, cin = 0, cout = 0;
   int fc_in = 0, fc_out = 0;
   int* kernel_status = nullptr;  // device word set by a tcgen05 kernel whose mbarrier wait timed out
+  int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
+  std::vector<cudaEvent_t> ev_beg, ev_end;
   std::vector<void*> owned;  // device allocations to free
 };
 
@@ -414,6 +416,8 @@ void p2m_model_destroy(p2m_model_t* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (void* p : m->owned) cudaFree(p);
+  for (cudaEvent_t e : m->ev_beg) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_end) cudaEventDestroy(e);
   delete m;
 }
 
@@ -439,6 +443,37 @@ int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out) {
   int v = 0;
   P2M_CUDA_OK(cudaMemcpy(&v, m->kernel_status, sizeof(int), cudaMemcpyDeviceToHost));
   *out = v;
+  return P2M_OK;
+}
+
+int p2m_model_set_profiling(p2m_model_t* m, int enable) {
+  if (!m) {
+    set_error("set_profiling: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  P2M_CUDA_OK(cudaSetDevice(m->device));
+  if (enable && m->ev_beg.empty()) {
+    m->ev_beg.resize(m->layers.size());
+    m->ev_end.resize(m->layers.size());
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+      P2M_CUDA_OK(cudaEventCreate(&m->ev_beg[i]));
+      P2M_CUDA_OK(cudaEventCreate(&m->ev_end[i]));
+    }
+  }
+  m->profiling = enable ? 1 : 0;
+  return P2M_OK;
+}
+
+int p2m_model_layer_times_ms(p2m_model_t* m, float* out, int n) {
+  if (!m || !out || n < (int)m->layers.size() || m->ev_beg.empty()) {
+    set_error("layer_times_ms: profiling was not enabled or buffer too small");
+    return P2M_ERR_INVALID;
+  }
+  P2M_CUDA_OK(cudaSetDevice(m->device));
+  for (size_t i = 0; i < m->layers.size(); ++i) {
+    P2M_CUDA_OK(cudaEventSynchronize(m->ev_end[i]));
+    P2M_CUDA_OK(cudaEventElapsedTime(&out[i], m->ev_beg[i], m->ev_end[i]));
+  }
   return P2M_OK;
 }
 
@@ -528,7 +563,9 @@ int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, f
             }
           out = w.rot[out_buf];
         }
+        if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_beg[li], s));
         P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s));
+        if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_end[li], s));
         cur = out;
         cur_buf = out_buf;
         cur_unpool = 0;

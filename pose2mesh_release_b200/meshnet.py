@@ -94,6 +94,27 @@ class BakedHierarchy:
             for h in self._handles.values():
                 _lib.check(_lib.load().p2m_model_set_precision(h, precision), "p2m_model_set_precision")
 
+    def set_profiling(self, device_index: int, enable: bool):
+        _lib.check(_lib.load().p2m_model_set_profiling(self.handle(device_index), int(enable)), "set_profiling")
+
+    def layer_info(self, device_index: int):
+        lib = _lib.load()
+        h = self.handle(device_index)
+        out = []
+        for i in range(lib.p2m_model_num_layers(h)):
+            buf = (C.c_int32 * 6)()
+            _lib.check(lib.p2m_model_layer_info(h, i, buf), "layer_info")
+            out.append(dict(level=buf[0], V=buf[1], fin=buf[2], fout=buf[3], bn=buf[4], relu=buf[5]))
+        return out
+
+    def layer_times_ms(self, device_index: int):
+        lib = _lib.load()
+        h = self.handle(device_index)
+        n = lib.p2m_model_num_layers(h)
+        buf = (C.c_float * n)()
+        _lib.check(lib.p2m_model_layer_times_ms(h, buf, n), "layer_times_ms")
+        return list(buf)
+
     def kernel_status(self, device_index: int) -> int:
         """0 unless a tcgen05 kernel's bounded mbarrier wait timed out (debug aid; synchronises)."""
         out = C.c_int32(0)
