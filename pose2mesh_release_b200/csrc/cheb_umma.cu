@@ -46,16 +46,14 @@ struct TileHeader {  // 64 bytes
   int n_rows;     // valid vertices in this tile (<= 128)
   int h1;         // rows of T1 kept on chip: 128 tile slots + 1-hop halo
   int h2;         // rows of X staged: h1 + 2-hop halo
-  int nnz_a, nnz_b;
-  int off_halo;   // int32 [h2]   vertex id of staged row i (-1: empty slot)
-  int off_rpa;    // uint16 [h1+1] CSR over T1 rows, columns index staged X rows
-  int off_idxa;   // uint16 [nnz_a]
-  int off_vala;   // float  [nnz_a]
-  int off_rpb;    // uint16 [129]  CSR over the 128 tile rows, columns index T1 rows
-  int off_idxb;   // uint16 [nnz_b]
-  int off_valb;   // float  [nnz_b]
+  int nnz;
+  int off_halo;   // int32 [h2]    vertex id of staged row i (-1: empty slot)
+  int off_rp;     // uint16 [h1+1] local CSR: row i < h1 lists the neighbours of vertex halo[i]
+  int off_ent;    // uint2 [nnz]   {byte offset of the neighbour's staged row (slot*128), value bits}
+  int off_ord1;   // uint16 [h1]   T1 rows sorted by decreasing length (warps see equal trip counts)
+  int off_ord2;   // uint16 [128]  tile rows sorted by decreasing length
   int bytes;
-  int pad[3];
+  int pad[6];
 };
 static_assert(sizeof(TileHeader) == 64, "header size");
 
@@ -86,11 +84,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must not hang the GPU box.  On timeout the CTA-wide abort flag is
 // raised, the global status word is set and every later wait falls through immediately.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status,
                                           int code) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
-    if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+      if (mbar_try_wait(bar, parity)) return;
+    }
     if (*abort_flag) return;
+    if (global_ns() - t0 > 400000000ull) break;  // 0.4 s: far beyond any legitimate wait
   }
   *abort_flag = 1;
   atomicExch(status, code);
@@ -111,7 +120,50 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// explicit shared-window accesses (32-bit addresses): keeps the hot loops on LDS/STS instead of generic LD/ST
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, const uint2& v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
+  acc.x = fmaf(w, x.x, acc.x);
+  acc.y = fmaf(w, x.y, acc.y);
+  acc.z = fmaf(w, x.z, acc.z);
+  acc.w = fmaf(w, x.w, acc.w);
+}
+// acc += sum_e val[e] * rows[slot[e]][q]  over the CSR entries [e, e1) of one row; `rows` = staged X or T1
+__device__ __forceinline__ float4 gather_row(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; e + 1 < e1; e += 2) {
+    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8);
+    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x);
+    fma4(acc, __uint_as_float(a0.y), x0);
+    fma4(acc, __uint_as_float(a1.y), x1);
+  }
+  if (e < e1) {
+    const uint2 a0 = lds_u2(ent + e * 8);
+    fma4(acc, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
+  }
+  return acc;
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
@@ -188,220 +240,299 @@ struct KParams {
   const float* x;
   int in_unpool;
   int V, P, fin;
+  int n_tiles;
   const unsigned char* meta;
   const int* meta_bytes;
   int meta_stride, max_h1, max_h2;
   const unsigned char* wpack;
+  const float* zero_row;  // 128 bytes of zeros: source of the empty halo slots of ragged tiles
   EpiDev ep;
+  int res_identity;       // residual resampling is the identity (Fin_block == Fout): vector path
   float* y;
   int* status;
 };
 
-// =====================================================================================
-template <int N, int NS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_cheb_conv_umma(const KParams p) {
+// Warp roles (23 warps, one persistent CTA per SM):
+//   0..15  producers: SpMM out of shared memory + fp16 (hi,lo) split + swizzled A-block stores
+//   16     halo loader: per (tile, chunk) one cp.async.bulk per staged X row, per tile the metadata blob
+//   17     weight-block loader (one thread, cp.async.bulk)
+//   18     MMA issuer (one thread) and TMEM owner
+//   19..22 epilogue: TMEM -> registers -> fused epilogue -> HBM, overlapped with the next tile's main loop
+constexpr int W_PROD = 16;
+constexpr int W_XLOAD = 16, W_BLOAD = 17, W_MMA = 18, W_EPI0 = 19;
+constexpr int NUM_THREADS2 = 23 * 32;
+
+template <int N, int NS, int XS>
+__global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParams p) {
   constexpr int B_BLOCK_BYTES = N * 128;
   constexpr int SLOT_BYTES = A_BLOCK_BYTES + B_BLOCK_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16(TILE_M, N);
-  constexpr int TMEM_COLS = N < 32 ? 32 : N;
+  constexpr int TMEM_COLS = 2 * N;  // double-buffered accumulator (N = 64/128/256 -> 128/256/512 columns)
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* ring = smem;
-  float* Xs = reinterpret_cast<float*>(ring + NS * SLOT_BYTES);
-  float* T1s = Xs + (size_t)p.max_h2 * FC;
-  unsigned char* meta_s = reinterpret_cast<unsigned char*>(T1s + (size_t)p.max_h1 * FC);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(meta_s + p.meta_stride);
-  // bars: full[NS], empty[NS], accum_full, meta_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+  unsigned char* ring = smem_raw;  // 128B-swizzled blocks need 1024-byte alignment (checked below)
+  float* Xs = reinterpret_cast<float*>(ring + NS * SLOT_BYTES);                 // [XS][max_h2][32]
+  const size_t xs_stage_floats = (size_t)p.max_h2 * FC;
+  float* T1s = Xs + XS * xs_stage_floats;                                       // [max_h1][32]
+  unsigned char* meta_s = reinterpret_cast<unsigned char*>(T1s + (size_t)p.max_h1 * FC);  // [2][meta_stride]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta_s + 2 * (size_t)p.meta_stride);
+  // barrier map
+  uint64_t* b_ab_full = bars;                // [NS]
+  uint64_t* b_ab_empty = b_ab_full + NS;     // [NS]
+  uint64_t* b_x_full = b_ab_empty + NS;      // [XS]
+  uint64_t* b_x_empty = b_x_full + XS;       // [XS]
+  uint64_t* b_m_full = b_x_empty + XS;       // [2]
+  uint64_t* b_m_empty = b_m_full + 2;        // [2]
+  uint64_t* b_acc_full = b_m_empty + 2;      // [2]
+  uint64_t* b_acc_empty = b_acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_acc_empty + 2);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int tile = blockIdx.x;
-  const int b = tile / p.P;
-  const int pat = tile - b * p.P;
-  const long long mesh_row0 = (long long)b * p.V;
+  const int lane = tid & 31;
   const int n_chunk = p.fin / FC;
   const int n_use = 3 * n_chunk;
 
-  const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = smem_u32(bars + NS);
-  const uint32_t bar_accum = smem_u32(bars + 2 * NS);
-  const uint32_t bar_meta = smem_u32(bars + 2 * NS + 1);
-
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(bar_full + 8 * s, NUM_WORKERS + 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(smem_u32(b_ab_full + s), W_PROD * 32 + 1);
+      mbar_init(smem_u32(b_ab_empty + s), 1);
     }
-    mbar_init(bar_accum, 1);
-    mbar_init(bar_meta, 1);
-    *abort_flag = 0;
+    for (int s = 0; s < XS; ++s) {
+      mbar_init(smem_u32(b_x_full + s), 1);
+      mbar_init(smem_u32(b_x_empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(b_m_full + s), 1);
+      mbar_init(smem_u32(b_m_empty + s), 1);
+      mbar_init(smem_u32(b_acc_full + s), 1);
+      mbar_init(smem_u32(b_acc_empty + s), 4);
+    }
+    *abort_flag = (smem_u32(ring) & 1023u) ? 1 : 0;
+    if (*abort_flag) atomicExch(p.status, 100);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    // ------------------------------------------------------------ weight-block loader (one thread)
-    if ((tid & 31) == 0) {
-      const int mbytes = p.meta_bytes[pat];
-      mbar_arrive_expect_tx(bar_meta, mbytes);
-      bulk_g2s(smem_u32(meta_s), p.meta + (size_t)pat * p.meta_stride, mbytes, bar_meta);
-      for (int u = 0; u < n_use; ++u) {
-        const int s = u % NS, round = u / NS;
-        mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1, abort_flag, p.status, 1);
-        mbar_arrive_expect_tx(bar_full + 8 * s, B_BLOCK_BYTES);
-        bulk_g2s(smem_u32(ring + s * SLOT_BYTES + A_BLOCK_BYTES), p.wpack + (size_t)u * B_BLOCK_BYTES, B_BLOCK_BYTES,
-                 bar_full + 8 * s);
+  if (warp == W_XLOAD) {
+    // ------------------------------------------------------------ halo / metadata loader
+    uint32_t xcnt = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.P, pat = tile - b * p.P;
+      const int m = it & 1;
+      const uint32_t mpar = (it >> 1) & 1;
+      unsigned char* mdst = meta_s + (size_t)m * p.meta_stride;
+      if (lane == 0) {
+        mbar_wait(smem_u32(b_m_empty + m), mpar ^ 1, abort_flag, p.status, 1);
+        const int mbytes = p.meta_bytes[pat];
+        mbar_arrive_expect_tx(smem_u32(b_m_full + m), mbytes);
+        bulk_g2s(smem_u32(mdst), p.meta + (size_t)pat * p.meta_stride, mbytes, smem_u32(b_m_full + m));
+      }
+      mbar_wait(smem_u32(b_m_full + m), mpar, abort_flag, p.status, 2);
+      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mdst);
+      const int h2 = hdr->h2;
+      const int* halo = reinterpret_cast<const int*>(mdst + hdr->off_halo);
+      const long long mesh_row0 = (long long)b * p.V;
+      for (int c = 0; c < n_chunk; ++c, ++xcnt) {
+        const int xs = xcnt % XS;
+        const uint32_t xpar = (xcnt / XS) & 1;
+        const uint32_t bar = smem_u32(b_x_full + xs);
+        if (lane == 0) {
+          mbar_wait(smem_u32(b_x_empty + xs), xpar ^ 1, abort_flag, p.status, 3);
+          mbar_arrive_expect_tx(bar, (uint32_t)h2 * 128u);
+        }
+        __syncwarp();
+        float* xdst = Xs + xs * xs_stage_floats;
+        for (int i = lane; i < h2; i += 32) {
+          const int v = halo[i];
+          const float* src = p.zero_row;
+          if (v >= 0) {
+            long long r = mesh_row0 + v;
+            if (p.in_unpool) r >>= 1;
+            src = p.x + r * p.fin + c * FC;
+          }
+          bulk_g2s(smem_u32(xdst + (size_t)i * FC), src, 128u, bar);
+        }
       }
     }
-  } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if ((tid & 31) == 0) {
-      for (int u = 0; u < n_use; ++u) {
-        const int s = u % NS, round = u / NS;
-        mbar_wait(bar_full + 8 * s, round & 1, abort_flag, p.status, 2);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(ring + s * SLOT_BYTES);
-        const uint32_t b0 = a0 + A_BLOCK_BYTES;
-        const uint64_t da = make_desc_sw128(a0), db = make_desc_sw128(b0);
-        // A block columns: [hi 0..31 | lo 32..63], B block columns: [Whi 0..31 | Wlo 32..63] (fp16);
-        // a 16-element K step is 32 bytes = +2 in the descriptor's start-address field.
-        //   hi*Whi            lo*Whi            hi*Wlo
-        umma_f16(tmem_base, da + 0, db + 0, IDESC, u > 0);
-        umma_f16(tmem_base, da + 2, db + 2, IDESC, 1);
-        umma_f16(tmem_base, da + 4, db + 0, IDESC, 1);
-        umma_f16(tmem_base, da + 6, db + 2, IDESC, 1);
-        umma_f16(tmem_base, da + 0, db + 4, IDESC, 1);
-        umma_f16(tmem_base, da + 2, db + 6, IDESC, 1);
-        umma_commit(bar_empty + 8 * s);  // frees the slot when these MMAs have read it
+  } else if (warp == W_BLOAD) {
+    // ------------------------------------------------------------ weight-block loader (one thread)
+    if (lane == 0) {
+      uint32_t ucnt = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int u = 0; u < n_use; ++u, ++ucnt) {
+          const int s = ucnt % NS;
+          const uint32_t par = (ucnt / NS) & 1;
+          mbar_wait(smem_u32(b_ab_empty + s), par ^ 1, abort_flag, p.status, 4);
+          mbar_arrive_expect_tx(smem_u32(b_ab_full + s), B_BLOCK_BYTES);
+          bulk_g2s(smem_u32(ring + s * SLOT_BYTES + A_BLOCK_BYTES), p.wpack + (size_t)u * B_BLOCK_BYTES, B_BLOCK_BYTES,
+                   smem_u32(b_ab_full + s));
+        }
       }
-      umma_commit(bar_accum);
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t ucnt = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(smem_u32(b_acc_empty + as), ((it >> 1) & 1) ^ 1, abort_flag, p.status, 5);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
+        for (int u = 0; u < n_use; ++u, ++ucnt) {
+          const int s = ucnt % NS;
+          mbar_wait(smem_u32(b_ab_full + s), (ucnt / NS) & 1, abort_flag, p.status, 6);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(ring + s * SLOT_BYTES);
+          const uint64_t da = make_desc_sw128(a0), db = make_desc_sw128(a0 + A_BLOCK_BYTES);
+          // A block columns: [hi 0..31 | lo 32..63], B block columns: [Whi 0..31 | Wlo 32..63] (fp16);
+          // a 16-element K step is 32 bytes = +2 in the descriptor's start-address field.
+          umma_f16(d_tmem, da + 0, db + 0, IDESC, u > 0);  // hi * Whi
+          umma_f16(d_tmem, da + 2, db + 2, IDESC, 1);
+          umma_f16(d_tmem, da + 4, db + 0, IDESC, 1);      // lo * Whi
+          umma_f16(d_tmem, da + 6, db + 2, IDESC, 1);
+          umma_f16(d_tmem, da + 0, db + 4, IDESC, 1);      // hi * Wlo
+          umma_f16(d_tmem, da + 2, db + 6, IDESC, 1);
+          umma_commit(smem_u32(b_ab_empty + s));  // frees the slot when these MMAs have read it
+        }
+        umma_commit(smem_u32(b_acc_full + as));
+      }
+    }
+  } else if (warp >= W_EPI0) {
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> HBM
+    const int lane_base = (warp & 3) * 32;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int row_in_tile = lane_base + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.P, pat = tile - b * p.P;
+      const int as = it & 1;
+      const int n_rows = min(TILE_M, p.V - pat * TILE_M);
+      const long long r = (long long)b * p.V + (long long)pat * TILE_M + row_in_tile;
+      const bool valid = row_in_tile < n_rows;
+      float* yrow = p.y + r * N;
+      const float* res_row = nullptr;
+      if (p.ep.res != nullptr) res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
+      mbar_wait(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < N; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * N + cb), v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = cb + j;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = __uint_as_float(v[j + e]) * W_INV_SCALE;
+              if (p.ep.bias) t += p.ep.bias[n + e];
+              if (p.ep.scale) t = fmaf(t, p.ep.scale[n + e], p.ep.shift[n + e]);
+              if (p.ep.relu) t = fmaxf(t, 0.f);
+              o[e] = t;
+            }
+            if (res_row != nullptr) {
+              if (p.res_identity) {
+                const float4 rv = *reinterpret_cast<const float4*>(res_row + n);
+                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float l = p.ep.lam[n + e];
+                  o[e] += (1.f - l) * res_row[p.ep.i0[n + e]] + l * res_row[p.ep.i1[n + e]];
+                }
+              }
+            }
+            *reinterpret_cast<float4*>(yrow + n) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
     }
   } else {
-    // ------------------------------------------------------------ producers (8 warps)
-    mbar_wait(bar_meta, 0, abort_flag, p.status, 3);
-    const TileHeader* hdr = reinterpret_cast<const TileHeader*>(meta_s);
-    const int h1 = hdr->h1, h2 = hdr->h2;
-    const int* halo = reinterpret_cast<const int*>(meta_s + hdr->off_halo);
-    const unsigned short* rpa = reinterpret_cast<const unsigned short*>(meta_s + hdr->off_rpa);
-    const unsigned short* idxa = reinterpret_cast<const unsigned short*>(meta_s + hdr->off_idxa);
-    const float* vala = reinterpret_cast<const float*>(meta_s + hdr->off_vala);
-    const unsigned short* rpb = reinterpret_cast<const unsigned short*>(meta_s + hdr->off_rpb);
-    const unsigned short* idxb = reinterpret_cast<const unsigned short*>(meta_s + hdr->off_idxb);
-    const float* valb = reinterpret_cast<const float*>(meta_s + hdr->off_valb);
+    // ------------------------------------------------------------ producers (16 warps)
     const int q = tid & 7;     // float4 lane inside the 32-feature chunk
-    const int rg = tid >> 3;   // row group 0..31
-    const float4* Xs4 = reinterpret_cast<const float4*>(Xs);
-    float4* T1s4 = reinterpret_cast<float4*>(T1s);
+    const int rg = tid >> 3;   // row group 0..63
+    const uint32_t t1s_a = smem_u32(T1s);
+    const uint32_t ring_a = smem_u32(ring);
+    uint32_t xcnt = 0, ucnt = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int m = it & 1;
+      const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
+      mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 8);
+      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
+      const int h1 = hdr->h1;
+      const uint32_t mb_a = smem_u32(mb);
+      const uint32_t rp_a = mb_a + hdr->off_rp, ent_a = mb_a + hdr->off_ent;
+      const uint32_t ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
+      // the two tile rows this thread finishes (same for every chunk)
+      const uint32_t row0 = lds_u16(ord2_a + 2 * rg), row1 = lds_u16(ord2_a + 2 * (64 + rg));
+      const uint32_t r0e = lds_u16(rp_a + 2 * row0), r0e1 = lds_u16(rp_a + 2 * row0 + 2);
+      const uint32_t r1e = lds_u16(rp_a + 2 * row1), r1e1 = lds_u16(rp_a + 2 * row1 + 2);
 
-    for (int c = 0; c < n_chunk; ++c) {
-      // (1) stage the 2-hop halo of X for this feature chunk
-      for (int i = rg; i < h2; i += 32) {
-        const int v = halo[i];
-        const uint32_t dst = smem_u32(Xs + (size_t)i * FC + q * 4);
-        if (v >= 0) {
-          long long r = mesh_row0 + v;
-          if (p.in_unpool) r >>= 1;
-          cp_async16(dst, p.x + r * p.fin + c * FC + q * 4);
-        } else {
-          *reinterpret_cast<float4*>(Xs + (size_t)i * FC + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < n_chunk; ++c, ++xcnt) {
+        const int xs = xcnt % XS;
+        mbar_wait(smem_u32(b_x_full + xs), (xcnt / XS) & 1, abort_flag, p.status, 9);
+        const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
+        const uint32_t t1s_q = t1s_a + q * 16;
+        // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows)
+        for (int j = rg; j < h1; j += 64) {
+          const uint32_t i = lds_u16(ord1_a + 2 * j);
+          const uint32_t e = lds_u16(rp_a + 2 * i), e1 = lds_u16(rp_a + 2 * i + 2);
+          sts_f4(t1s_q + i * 128, gather_row(ent_a, e, e1, xs_q));
         }
-      }
-      cp_async_wait_all();
-      worker_barrier();
-      // (2) T1 = L~ X on the tile rows and their 1-hop halo
-      for (int i = rg; i < h1; i += 32) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int e1 = rpa[i + 1];
-        for (int e = rpa[i]; e < e1; ++e) {
-          const float w = vala[e];
-          const float4 xv = Xs4[(size_t)idxa[e] * 8 + q];
-          acc.x = fmaf(w, xv.x, acc.x);
-          acc.y = fmaf(w, xv.y, acc.y);
-          acc.z = fmaf(w, xv.z, acc.z);
-          acc.w = fmaf(w, xv.w, acc.w);
+        producer_barrier();
+        // (2) T2 = 2 L~ T1 - X on the tile rows (a tile row's neighbours all have a T1 slot)
+        float4 t0[2], t1[2], t2[2];
+        {
+          const float4 g0 = gather_row(ent_a, r0e, r0e1, t1s_q);
+          const float4 g1 = gather_row(ent_a, r1e, r1e1, t1s_q);
+          t0[0] = lds_f4(xs_q + row0 * 128);
+          t0[1] = lds_f4(xs_q + row1 * 128);
+          t1[0] = lds_f4(t1s_q + row0 * 128);
+          t1[1] = lds_f4(t1s_q + row1 * 128);
+          t2[0] = make_float4(2.f * g0.x - t0[0].x, 2.f * g0.y - t0[0].y, 2.f * g0.z - t0[0].z, 2.f * g0.w - t0[0].w);
+          t2[1] = make_float4(2.f * g1.x - t0[1].x, 2.f * g1.y - t0[1].y, 2.f * g1.z - t0[1].z, 2.f * g1.w - t0[1].w);
         }
-        T1s4[(size_t)i * 8 + q] = acc;
-      }
-      worker_barrier();
-      // (3) T2 = 2 L~ T1 - X on the tile rows; split to fp16 hi/lo; write the three K-blocks
-      float4 t0[4], t1[4], t2[4];
+        // (3) split to fp16 (hi, lo) and write the three K-blocks into the A/B ring
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int i = ps * 32 + rg;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int e1 = rpb[i + 1];
-        for (int e = rpb[i]; e < e1; ++e) {
-          const float w = valb[e];
-          const float4 tv = T1s4[(size_t)idxb[e] * 8 + q];
-          acc.x = fmaf(w, tv.x, acc.x);
-          acc.y = fmaf(w, tv.y, acc.y);
-          acc.z = fmaf(w, tv.z, acc.z);
-          acc.w = fmaf(w, tv.w, acc.w);
+        for (int k = 0; k < 3; ++k, ++ucnt) {
+          const int s = ucnt % NS;
+          mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
+          const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            const uint32_t i = ps ? row1 : row0;
+            const float4 v = (k == 0) ? t0[ps] : (k == 1 ? t1[ps] : t2[ps]);
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            sts_u2(ablk + sw128_off(i, q >> 1), hi);
+            sts_u2(ablk + sw128_off(i, 4 + (q >> 1)), lo);
+          }
+          fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(smem_u32(b_ab_full + s));
         }
-        t0[ps] = Xs4[(size_t)i * 8 + q];
-        t1[ps] = T1s4[(size_t)i * 8 + q];
-        t2[ps] = make_float4(2.f * acc.x - t0[ps].x, 2.f * acc.y - t0[ps].y, 2.f * acc.z - t0[ps].z,
-                             2.f * acc.w - t0[ps].w);
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int u = 3 * c + k;
-        const int s = u % NS, round = u / NS;
-        mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1, abort_flag, p.status, 4);
-        unsigned char* ablk = ring + s * SLOT_BYTES;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-          const int i = ps * 32 + rg;
-          const float4 v = (k == 0) ? t0[ps] : (k == 1 ? t1[ps] : t2[ps]);
-          uint2 hi, lo;
-          split4(v, hi, lo);
-          *reinterpret_cast<uint2*>(ablk + sw128_off(i, q >> 1) + (q & 1) * 8) = hi;
-          *reinterpret_cast<uint2*>(ablk + sw128_off(i, 4 + (q >> 1)) + (q & 1) * 8) = lo;
-        }
-        fence_async_proxy();  // make the generic-proxy stores visible to the tensor core (async proxy)
-        mbar_arrive(bar_full + 8 * s);
-      }
-      worker_barrier();  // Xs / T1s are overwritten by the next chunk
-    }
-
-    // ------------------------------------------------------------ epilogue: TMEM -> registers -> HBM
-    mbar_wait(bar_accum, 0, abort_flag, p.status, 5);
-    tc_fence_after();
-    const int lane_base = (warp & 3) * 32;
-    const int row_in_tile = lane_base + (tid & 31);
-    constexpr int COLS_PER_WARP = N / 2;
-    const int col0 = (warp >> 2) * COLS_PER_WARP;
-    const long long r = mesh_row0 + (long long)pat * TILE_M + row_in_tile;
-    const bool valid = row_in_tile < hdr->n_rows;
-    float* yrow = p.y + r * N;
-#pragma unroll 1
-    for (int cb = 0; cb < COLS_PER_WARP; cb += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + cb), v);
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          const int n = col0 + cb + j;
-          o.x = apply_epilogue(__uint_as_float(v[j + 0]) * W_INV_SCALE, r, n + 0, p.ep);
-          o.y = apply_epilogue(__uint_as_float(v[j + 1]) * W_INV_SCALE, r, n + 1, p.ep);
-          o.z = apply_epilogue(__uint_as_float(v[j + 2]) * W_INV_SCALE, r, n + 2, p.ep);
-          o.w = apply_epilogue(__uint_as_float(v[j + 3]) * W_INV_SCALE, r, n + 3, p.ep);
-          *reinterpret_cast<float4*>(yrow + n) = o;
+        producer_barrier();  // everybody is done with Xs[xs] and T1s
+        if (tid == 0) {
+          mbar_arrive(smem_u32(b_x_empty + xs));
+          if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == W_MMA) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // fp32 reference-layout weights [Fout, Fin*3] (column = f*3+k) -> K-blocks of fp16 [Whi | Wlo]
@@ -428,22 +559,22 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
   *reinterpret_cast<uint4*>(out + (size_t)u * fout * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
 }
 
-template <int N>
-struct RingCfg {
-  static constexpr int NS = (N == 256) ? 2 : 3;
-};
-
-size_t smem_bytes_for(int N, int NS, const DevLevel& g) {
-  return 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + (size_t)g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +
-         (size_t)g.meta_stride + 8 * (2 * NS + 2) + 16;
+size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g) {
+  return 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +
+         2 * (size_t)g.meta_stride + 8 * (2 * NS + 2 * XS + 8) + 16;
+}
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+inline int ring_stages(int N) { return N == 256 ? 2 : 3; }
+// X staging depth: 2 (prefetch the next chunk's halo during the current chunk) when it fits, else 1
+inline int x_stages(int N, const DevLevel& g) {
+  return smem_bytes_for(N, ring_stages(N), 2, g) <= SMEM_LIMIT ? 2 : 1;
 }
 
-template <int N>
-int launch_n(const UmmaConvArgs& a, int* status, cudaStream_t s) {
-  constexpr int NS = RingCfg<N>::NS;
+template <int N, int NS, int XS>
+int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   const DevLevel& g = *a.g;
-  const size_t smem = smem_bytes_for(N, NS, g);
-  auto kern = k_cheb_conv_umma<N, NS>;
+  const size_t smem = smem_bytes_for(N, NS, XS, g);
+  auto kern = k_cheb_conv_umma<N, NS, XS>;
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KParams p;
   p.x = a.x;
@@ -451,18 +582,29 @@ int launch_n(const UmmaConvArgs& a, int* status, cudaStream_t s) {
   p.V = g.V;
   p.P = g.n_pattern;
   p.fin = a.fin;
+  p.n_tiles = a.batch * g.n_pattern;
   p.meta = g.tile_meta;
   p.meta_bytes = g.tile_meta_bytes;
   p.meta_stride = g.meta_stride;
   p.max_h1 = g.max_h1;
   p.max_h2 = g.max_h2;
   p.wpack = static_cast<const unsigned char*>(a.wpack);
+  p.zero_row = zero_row;
   p.ep = to_dev(a.ep);
+  p.res_identity = (a.ep.res != nullptr && a.ep.res_F == a.fout) ? 1 : 0;
   p.y = a.y;
   p.status = status;
-  kern<<<a.batch * g.n_pattern, NUM_THREADS, smem, s>>>(p);
+  const int grid = std::min(p.n_tiles, sm_count);
+  kern<<<grid, NUM_THREADS2, smem, s>>>(p);
   P2M_LAUNCH_OK();
   return P2M_OK;
+}
+
+template <int N>
+int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
+  constexpr int NS = (N == 256) ? 2 : 3;
+  if (x_stages(N, *a.g) == 2) return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
+  return launch_cfg<N, NS, 1>(a, status, zero_row, sm_count, s);
 }
 
 }  // namespace
@@ -503,53 +645,52 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
       set_error("umma meta: halo too large");
       return P2M_ERR_INVALID;
     }
-    std::vector<unsigned short> rpa(h1 + 1, 0), idxa, rpb(TILE_M + 1, 0), idxb;
-    std::vector<float> vala, valb;
+    // One local CSR serves both products: row i < h1 lists (staged-row slot, value) of vertex halo[i].
+    // T1 rows read X slots (< h2); the T2 pass only walks the 128 tile rows, whose columns are < h1,
+    // i.e. valid T1 slots (slot numbering of X and T1 coincides below h1).
+    std::vector<unsigned short> rp(h1 + 1, 0);
+    std::vector<unsigned int> ent;  // pairs {slot*128, float bits}
     for (int i = 0; i < h1; ++i) {
       if (halo[i] >= 0)
         for (int e = rowptr[halo[i]]; e < rowptr[halo[i] + 1]; ++e) {
-          idxa.push_back((unsigned short)slot_of[colidx[e]]);
-          vala.push_back(val[e]);
+          unsigned int bits;
+          std::memcpy(&bits, &val[e], 4);
+          ent.push_back((unsigned int)slot_of[colidx[e]] * 128u);
+          ent.push_back(bits);
         }
-      rpa[i + 1] = (unsigned short)idxa.size();
+      rp[i + 1] = (unsigned short)(ent.size() / 2);
     }
-    for (int i = 0; i < TILE_M; ++i) {
-      if (i < n_rows)
-        for (int e = rowptr[v0 + i]; e < rowptr[v0 + i + 1]; ++e) {
-          idxb.push_back((unsigned short)slot_of[colidx[e]]);  // < h1 by construction
-          valb.push_back(val[e]);
-        }
-      rpb[i + 1] = (unsigned short)idxb.size();
-    }
-    if (idxa.size() > 65535) {
+    const int nnz = (int)(ent.size() / 2);
+    if (nnz > 65535) {
       set_error("umma meta: too many entries in a tile");
       return P2M_ERR_INVALID;
     }
+    auto row_len = [&](int i) { return (int)rp[i + 1] - (int)rp[i]; };
+    std::vector<unsigned short> ord1(h1), ord2(TILE_M);
+    for (int i = 0; i < h1; ++i) ord1[i] = (unsigned short)i;
+    for (int i = 0; i < TILE_M; ++i) ord2[i] = (unsigned short)i;
+    std::stable_sort(ord1.begin(), ord1.end(), [&](unsigned short a, unsigned short b2) { return row_len(a) > row_len(b2); });
+    std::stable_sort(ord2.begin(), ord2.end(), [&](unsigned short a, unsigned short b2) { return row_len(a) > row_len(b2); });
     TileHeader h{};
     h.n_rows = n_rows;
     h.h1 = h1;
     h.h2 = h2;
-    h.nnz_a = (int)idxa.size();
-    h.nnz_b = (int)idxb.size();
+    h.nnz = nnz;
     int off = 64;
     h.off_halo = off; off += up16(h2 * 4);
-    h.off_rpa = off;  off += up16((h1 + 1) * 2);
-    h.off_idxa = off; off += up16(h.nnz_a * 2);
-    h.off_vala = off; off += up16(h.nnz_a * 4);
-    h.off_rpb = off;  off += up16((TILE_M + 1) * 2);
-    h.off_idxb = off; off += up16(h.nnz_b * 2);
-    h.off_valb = off; off += up16(h.nnz_b * 4);
+    h.off_rp = off;   off += up16((h1 + 1) * 2);
+    h.off_ent = off;  off += up16(nnz * 8);
+    h.off_ord1 = off; off += up16(h1 * 2);
+    h.off_ord2 = off; off += up16(TILE_M * 2);
     h.bytes = off;
     std::vector<unsigned char>& blob = blobs[pt];
     blob.assign(off, 0);
     std::memcpy(blob.data(), &h, sizeof(h));
     std::memcpy(blob.data() + h.off_halo, halo.data(), h2 * 4);
-    std::memcpy(blob.data() + h.off_rpa, rpa.data(), (h1 + 1) * 2);
-    if (h.nnz_a) std::memcpy(blob.data() + h.off_idxa, idxa.data(), h.nnz_a * 2);
-    if (h.nnz_a) std::memcpy(blob.data() + h.off_vala, vala.data(), h.nnz_a * 4);
-    std::memcpy(blob.data() + h.off_rpb, rpb.data(), (TILE_M + 1) * 2);
-    if (h.nnz_b) std::memcpy(blob.data() + h.off_idxb, idxb.data(), h.nnz_b * 2);
-    if (h.nnz_b) std::memcpy(blob.data() + h.off_valb, valb.data(), h.nnz_b * 4);
+    std::memcpy(blob.data() + h.off_rp, rp.data(), (h1 + 1) * 2);
+    if (nnz) std::memcpy(blob.data() + h.off_ent, ent.data(), (size_t)nnz * 8);
+    std::memcpy(blob.data() + h.off_ord1, ord1.data(), h1 * 2);
+    std::memcpy(blob.data() + h.off_ord2, ord2.data(), TILE_M * 2);
     max_h1 = std::max(max_h1, h1);
     max_h2 = std::max(max_h2, h2);
     stride = std::max(stride, off);
@@ -584,8 +725,7 @@ bool umma_conv_supported(const DevLevel& g, int fin, int fout) {
   if (g.tile_meta == nullptr || g.n_pattern <= 0) return false;
   if (fin % FC != 0 || fin < FC || fin > 256) return false;
   if (fout != 64 && fout != 128 && fout != 256) return false;
-  const int ns = (fout == 256) ? 2 : 3;
-  return smem_bytes_for(fout, ns, g) <= 227 * 1024;
+  return smem_bytes_for(fout, ring_stages(fout), 1, g) <= SMEM_LIMIT;
 }
 
 size_t umma_wpack_bytes(int fin, int fout) { return (size_t)(fin / FC) * 3 * fout * 128; }
@@ -597,15 +737,15 @@ int launch_umma_pack_weights(const float* W, int fin, int fout, void* wpack, cud
   return P2M_OK;
 }
 
-int launch_umma_conv(const UmmaConvArgs& a, int* status, cudaStream_t s) {
+int launch_umma_conv(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   if (!umma_conv_supported(*a.g, a.fin, a.fout)) {
     set_error("umma_conv: unsupported shape");
     return P2M_ERR_INVALID;
   }
   switch (a.fout) {
-    case 64: return launch_n<64>(a, status, s);
-    case 128: return launch_n<128>(a, status, s);
-    case 256: return launch_n<256>(a, status, s);
+    case 64: return launch_n<64>(a, status, zero_row, sm_count, s);
+    case 128: return launch_n<128>(a, status, zero_row, sm_count, s);
+    case 256: return launch_n<256>(a, status, zero_row, sm_count, s);
   }
   return P2M_ERR_INVALID;
 }

@@ -338,6 +338,122 @@ int launch_gemm_tn_atomic(const float* A, int lda, const float* B, int ldb, floa
   return P2M_OK;
 }
 
+
+// =====================================================================================
+// Thin-output Chebyshev conv (Fout <= 4, the 64 -> 3 head of the network), weights first:
+//   Y = X (W0 - W2) + L~ ( X W1 + 2 L~ (X W2) ) + b
+// algebraically identical to [T0|T1|T2] W^T (T2 = 2 L~ L~ X - X) but the SpMMs act on 3-wide rows
+// instead of Fin-wide ones, and the basis is never materialised: HBM traffic = read X once.
+// =====================================================================================
+// transformed weights wt[f][j], j = 4*k' + n (n < fout <= 4):  k'=0: W0-W2, 1: W1, 2: W2
+
+__global__ void k_thin_prep(const float* __restrict__ W, int fin, int fout, float* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= fin * 12) return;
+  int f = idx / 12, j = idx % 12, kk = j / 4, n = j % 4;
+  float v = 0.f;
+  if (n < fout) {
+    const float* wr = W + (size_t)n * fin * 3 + (size_t)f * 3;  // reference layout: column = f*3 + k
+    v = (kk == 0) ? (wr[0] - wr[2]) : wr[kk];
+  }
+  out[idx] = v;
+}
+
+// Z[r][12] = X[r][:] * Wt ; one thread per row, rows staged through shared memory (coalesced loads).
+template <int FIN>
+__global__ void __launch_bounds__(128) k_thin_gemm(const float* __restrict__ x, int in_unpool, long long rows,
+                                                   const float* __restrict__ wt, float* __restrict__ Z) {
+  __shared__ float xs[128][FIN + 1];
+  __shared__ float ws[FIN * 12];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < FIN * 12; i += 128) ws[i] = wt[i];
+  const long long r0 = (long long)blockIdx.x * 128;
+  for (int e = tid; e < 128 * (FIN / 4); e += 128) {
+    const int row = e / (FIN / 4), c4 = e % (FIN / 4);
+    const long long r = r0 + row;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) v = reinterpret_cast<const float4*>(x + (in_unpool ? (r >> 1) : r) * FIN)[c4];
+    xs[row][c4 * 4 + 0] = v.x;
+    xs[row][c4 * 4 + 1] = v.y;
+    xs[row][c4 * 4 + 2] = v.z;
+    xs[row][c4 * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  float acc[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+#pragma unroll 4
+  for (int f = 0; f < FIN; ++f) {
+    const float xv = xs[tid][f];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = fmaf(xv, ws[f * 12 + j], acc[j]);
+  }
+  const long long r = r0 + tid;
+  if (r < rows) {
+    float4* zr = reinterpret_cast<float4*>(Z + r * 12);
+    zr[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    zr[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    zr[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+  }
+}
+
+// U = Z1 + 2 L~ Z2   (written over the Z1 slot is not possible: neighbours still need Z2; separate buffer)
+__global__ void __launch_bounds__(256) k_thin_u(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                const float* __restrict__ val, int V, long long rows,
+                                                const float* __restrict__ Z, float* __restrict__ U) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int v = (int)(r % V);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) {
+    const float4 z2 = reinterpret_cast<const float4*>(Z + (r + reloff[p]) * 12)[2];
+    const float w = 2.f * val[p];
+    acc.x = fmaf(w, z2.x, acc.x); acc.y = fmaf(w, z2.y, acc.y); acc.z = fmaf(w, z2.z, acc.z); acc.w = fmaf(w, z2.w, acc.w);
+  }
+  const float4 z1 = reinterpret_cast<const float4*>(Z + r * 12)[1];
+  reinterpret_cast<float4*>(U)[r] = make_float4(acc.x + z1.x, acc.y + z1.y, acc.z + z1.z, acc.w + z1.w);
+}
+
+__global__ void __launch_bounds__(256) k_thin_out(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                  const float* __restrict__ val, int V, long long rows, int fout,
+                                                  const float* __restrict__ Z, const float* __restrict__ U, EpiDev ep,
+                                                  float* __restrict__ y) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int v = (int)(r % V);
+  float4 acc = reinterpret_cast<const float4*>(Z + r * 12)[0];
+  for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) {
+    const float4 u = reinterpret_cast<const float4*>(U)[r + reloff[p]];
+    const float w = val[p];
+    acc.x = fmaf(w, u.x, acc.x); acc.y = fmaf(w, u.y, acc.y); acc.z = fmaf(w, u.z, acc.z); acc.w = fmaf(w, u.w, acc.w);
+  }
+  const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+  for (int n = 0; n < fout; ++n) y[r * fout + n] = apply_epilogue(o[n], r, n, ep);
+}
+
+bool thin_conv_supported(int fin, int fout) { return fout <= 4 && (fin == 64 || fin == 32); }
+size_t thin_conv_scratch_floats(long long rows, int fin) { return (size_t)rows * 16 + (size_t)fin * 12; }
+
+int launch_thin_conv(const DevLevel& g, const float* x, int in_unpool, int rows, int fin, int fout, const float* W,
+                     const Epilogue& e, float* scratch, float* y, cudaStream_t s) {
+  float* Z = scratch;                       // [rows][12]
+  float* U = Z + (size_t)rows * 12;         // [rows][4]
+  float* wt = U + (size_t)rows * 4;         // [fin][12]
+  k_thin_prep<<<cdiv(fin * 12, 128), 128, 0, s>>>(W, fin, fout, wt);
+  P2M_LAUNCH_OK();
+  const int grid = cdiv(rows, 128);
+  if (fin == 64)
+    k_thin_gemm<64><<<grid, 128, 0, s>>>(x, in_unpool, rows, wt, Z);
+  else
+    k_thin_gemm<32><<<grid, 128, 0, s>>>(x, in_unpool, rows, wt, Z);
+  P2M_LAUNCH_OK();
+  k_thin_u<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, Z, U);
+  P2M_LAUNCH_OK();
+  k_thin_out<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, fout, Z, U, to_dev(e), y);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
 // =====================================================================================
 // small helpers
 // =====================================================================================

@@ -48,6 +48,7 @@ struct p2m_model {
   int n_joint = 0, cin = 0, cout = 0;
   int fc_in = 0, fc_out = 0;
   int* kernel_status = nullptr;  // device word set by a tcgen05 kernel whose mbarrier wait timed out
+  float* zero_row = nullptr;     // 128 B of zeros (halo source for the empty slots of ragged tiles)
   int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
   std::vector<cudaEvent_t> ev_beg, ev_end;
   std::vector<void*> owned;  // device allocations to free
@@ -239,7 +240,11 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
     a.wpack = wpack;
     a.ep = ep;
     a.y = y;
-    return launch_umma_conv(a, m->kernel_status, s);
+    return launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s);
+  }
+  if (thin_conv_supported(L.fin, L.fout) && ep.res == nullptr &&
+      thin_conv_scratch_floats(rows, L.fin) <= (size_t)rows * 3 * L.fin) {
+    return launch_thin_conv(g, x, in_unpool, rows, L.fin, L.fout, w_ref, ep, T, y, s);  // T doubles as scratch
   }
   P2M_TRY(launch_cheb_basis(g, x, in_unpool, rows, L.fin, T, s));
   P2M_TRY(launch_gemm(T, 3 * L.fin, wp, 3 * L.fin, 0, y, L.fout, rows, L.fout, 3 * L.fin, ep, s));
@@ -333,7 +338,9 @@ int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
   }
   {
     std::vector<int> zero(1, 0);
+    std::vector<float> zrow(64, 0.f);
     int st = upload(m, zero, &m->kernel_status);
+    if (!st) st = upload(m, zrow, &m->zero_row);
     if (st) {
       p2m_model_destroy(m);
       return st;

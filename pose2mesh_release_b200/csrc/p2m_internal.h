@@ -126,6 +126,12 @@ int launch_gemm(const float* A, int lda, const float* B, int ldb, int b_is_kn, f
 int launch_gemm_tn_atomic(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N1, int N2,
                           cudaStream_t s);
 
+// Thin-output conv (Fout <= 4), weights first; scratch >= thin_conv_scratch_floats(rows, fin) floats.
+bool thin_conv_supported(int fin, int fout);
+size_t thin_conv_scratch_floats(long long rows, int fin);
+int launch_thin_conv(const DevLevel& g, const float* x, int in_unpool, int rows, int fin, int fout, const float* W,
+                     const Epilogue& e, float* scratch, float* y, cudaStream_t s);
+
 int launch_permute_w(const float* W, float* Wp, int fout, int fin, cudaStream_t s);      // [n,f*3+k] -> [n,k*fin+f]
 int launch_unpermute_w(const float* Wp, float* W, int fout, int fin, cudaStream_t s);    // inverse
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
@@ -170,6 +176,6 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
 bool umma_conv_supported(const DevLevel& g, int fin, int fout);
 size_t umma_wpack_bytes(int fin, int fout);
 int launch_umma_pack_weights(const float* W /*[fout, fin*3] ref layout*/, int fin, int fout, void* wpack, cudaStream_t s);
-int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, cudaStream_t s);
+int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
 
 }  // namespace p2m
