@@ -117,6 +117,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  // the mbarrier gets this thread's arrival once all of its earlier cp.async copies have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -300,8 +304,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       mbar_init(smem_u32(b_ab_empty + s), 1);
     }
     for (int s = 0; s < XS; ++s) {
-      mbar_init(smem_u32(b_x_full + s), 1);
-      mbar_init(smem_u32(b_x_empty + s), 1);
+      mbar_init(smem_u32(b_x_full + s), W_PROD * 32);  // every producer thread: cp.async.mbarrier.arrive.noinc
+      mbar_init(smem_u32(b_x_empty + s), 1);           // (unused: the producers are also the consumers)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(b_m_full + s), 1);
@@ -320,45 +324,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == W_XLOAD) {
-    // ------------------------------------------------------------ halo / metadata loader
-    uint32_t xcnt = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int b = tile / p.P, pat = tile - b * p.P;
-      const int m = it & 1;
-      const uint32_t mpar = (it >> 1) & 1;
-      unsigned char* mdst = meta_s + (size_t)m * p.meta_stride;
-      if (lane == 0) {
-        mbar_wait(smem_u32(b_m_empty + m), mpar ^ 1, abort_flag, p.status, 1);
+    // ------------------------------------------------------------ tile-metadata loader (one thread, cp.async.bulk)
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int pat = tile % p.P;
+        const int m = it & 1;
+        mbar_wait(smem_u32(b_m_empty + m), ((it >> 1) & 1) ^ 1, abort_flag, p.status, 1);
         const int mbytes = p.meta_bytes[pat];
         mbar_arrive_expect_tx(smem_u32(b_m_full + m), mbytes);
-        bulk_g2s(smem_u32(mdst), p.meta + (size_t)pat * p.meta_stride, mbytes, smem_u32(b_m_full + m));
-      }
-      mbar_wait(smem_u32(b_m_full + m), mpar, abort_flag, p.status, 2);
-      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mdst);
-      const int h2 = hdr->h2;
-      const int* halo = reinterpret_cast<const int*>(mdst + hdr->off_halo);
-      const long long mesh_row0 = (long long)b * p.V;
-      for (int c = 0; c < n_chunk; ++c, ++xcnt) {
-        const int xs = xcnt % XS;
-        const uint32_t xpar = (xcnt / XS) & 1;
-        const uint32_t bar = smem_u32(b_x_full + xs);
-        if (lane == 0) {
-          mbar_wait(smem_u32(b_x_empty + xs), xpar ^ 1, abort_flag, p.status, 3);
-          mbar_arrive_expect_tx(bar, (uint32_t)h2 * 128u);
-        }
-        __syncwarp();
-        float* xdst = Xs + xs * xs_stage_floats;
-        for (int i = lane; i < h2; i += 32) {
-          const int v = halo[i];
-          const float* src = p.zero_row;
-          if (v >= 0) {
-            long long r = mesh_row0 + v;
-            if (p.in_unpool) r >>= 1;
-            src = p.x + r * p.fin + c * FC;
-          }
-          bulk_g2s(smem_u32(xdst + (size_t)i * FC), src, 128u, bar);
-        }
+        bulk_g2s(smem_u32(meta_s + (size_t)m * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
+                 smem_u32(b_m_full + m));
       }
     }
   } else if (warp == W_BLOAD) {
@@ -464,70 +440,97 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     const int rg = tid >> 3;   // row group 0..63
     const uint32_t t1s_a = smem_u32(T1s);
     const uint32_t ring_a = smem_u32(ring);
-    uint32_t xcnt = 0, ucnt = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_stage = my_tiles * n_chunk;  // flat sequence of (tile, chunk) stages of this CTA
+    uint32_t ucnt = 0;
+
+    // Stage the 2-hop halo of X for flat stage g into Xs[g % XS] with 16-byte cp.async copies (8 lanes per
+    // 128-byte row); completion is signalled on x_full[g % XS] by cp.async.mbarrier.arrive.noinc.
+    auto issue_halo_loads = [&](int g) {
+      const int it2 = g / n_chunk, c2 = g - it2 * n_chunk;
+      const int tile2 = blockIdx.x + it2 * gridDim.x;
+      const int b2 = tile2 / p.P;
+      const int m2 = it2 & 1;
+      if (c2 == 0) mbar_wait(smem_u32(b_m_full + m2), (it2 >> 1) & 1, abort_flag, p.status, 8);
+      const unsigned char* mb2 = meta_s + (size_t)m2 * p.meta_stride;
+      const TileHeader* hdr2 = reinterpret_cast<const TileHeader*>(mb2);
+      const int h2 = hdr2->h2;
+      const int* halo = reinterpret_cast<const int*>(mb2 + hdr2->off_halo);
+      const long long mesh_row0 = (long long)b2 * p.V;
+      const int xs2 = g % XS;
+      const uint32_t dst0 = smem_u32(Xs + xs2 * xs_stage_floats) + q * 16;
+      const float* src0 = p.x + c2 * FC + q * 4;
+      for (int i = rg; i < h2; i += 64) {
+        const int v = halo[i];
+        if (v >= 0) {
+          long long r = mesh_row0 + v;
+          if (p.in_unpool) r >>= 1;
+          cp_async16(dst0 + i * 128, src0 + r * p.fin);
+        } else {
+          sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+      cp_async_arrive_noinc(smem_u32(b_x_full + xs2));
+    };
+
+    if (n_stage > 0) issue_halo_loads(0);
+    for (int g = 0; g < n_stage; ++g) {
+      const int it = g / n_chunk, c = g - it * n_chunk;
       const int m = it & 1;
+      if (XS == 2 && g + 1 < n_stage) issue_halo_loads(g + 1);  // prefetch: overlaps this stage's SpMM
+      const int xs = g % XS;
+      mbar_wait(smem_u32(b_x_full + xs), (g / XS) & 1, abort_flag, p.status, 9);
+
       const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
-      mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 8);
       const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
       const int h1 = hdr->h1;
       const uint32_t mb_a = smem_u32(mb);
       const uint32_t rp_a = mb_a + hdr->off_rp, ent_a = mb_a + hdr->off_ent;
       const uint32_t ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
-      // the two tile rows this thread finishes (same for every chunk)
+      // the two tile rows this thread finishes
       const uint32_t row0 = lds_u16(ord2_a + 2 * rg), row1 = lds_u16(ord2_a + 2 * (64 + rg));
-      const uint32_t r0e = lds_u16(rp_a + 2 * row0), r0e1 = lds_u16(rp_a + 2 * row0 + 2);
-      const uint32_t r1e = lds_u16(rp_a + 2 * row1), r1e1 = lds_u16(rp_a + 2 * row1 + 2);
-
-      for (int c = 0; c < n_chunk; ++c, ++xcnt) {
-        const int xs = xcnt % XS;
-        mbar_wait(smem_u32(b_x_full + xs), (xcnt / XS) & 1, abort_flag, p.status, 9);
-        const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
-        const uint32_t t1s_q = t1s_a + q * 16;
-        // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows)
-        for (int j = rg; j < h1; j += 64) {
-          const uint32_t i = lds_u16(ord1_a + 2 * j);
-          const uint32_t e = lds_u16(rp_a + 2 * i), e1 = lds_u16(rp_a + 2 * i + 2);
-          sts_f4(t1s_q + i * 128, gather_row(ent_a, e, e1, xs_q));
-        }
-        producer_barrier();
-        // (2) T2 = 2 L~ T1 - X on the tile rows (a tile row's neighbours all have a T1 slot)
-        float4 t0[2], t1[2], t2[2];
-        {
-          const float4 g0 = gather_row(ent_a, r0e, r0e1, t1s_q);
-          const float4 g1 = gather_row(ent_a, r1e, r1e1, t1s_q);
-          t0[0] = lds_f4(xs_q + row0 * 128);
-          t0[1] = lds_f4(xs_q + row1 * 128);
-          t1[0] = lds_f4(t1s_q + row0 * 128);
-          t1[1] = lds_f4(t1s_q + row1 * 128);
-          t2[0] = make_float4(2.f * g0.x - t0[0].x, 2.f * g0.y - t0[0].y, 2.f * g0.z - t0[0].z, 2.f * g0.w - t0[0].w);
-          t2[1] = make_float4(2.f * g1.x - t0[1].x, 2.f * g1.y - t0[1].y, 2.f * g1.z - t0[1].z, 2.f * g1.w - t0[1].w);
-        }
-        // (3) split to fp16 (hi, lo) and write the three K-blocks into the A/B ring
-#pragma unroll
-        for (int k = 0; k < 3; ++k, ++ucnt) {
-          const int s = ucnt % NS;
-          mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
-          const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
-#pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            const uint32_t i = ps ? row1 : row0;
-            const float4 v = (k == 0) ? t0[ps] : (k == 1 ? t1[ps] : t2[ps]);
-            uint2 hi, lo;
-            split4(v, hi, lo);
-            sts_u2(ablk + sw128_off(i, q >> 1), hi);
-            sts_u2(ablk + sw128_off(i, 4 + (q >> 1)), lo);
-          }
-          fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(smem_u32(b_ab_full + s));
-        }
-        producer_barrier();  // everybody is done with Xs[xs] and T1s
-        if (tid == 0) {
-          mbar_arrive(smem_u32(b_x_empty + xs));
-          if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-        }
+      const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
+      const uint32_t t1s_q = t1s_a + q * 16;
+      // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows)
+      for (int j = rg; j < h1; j += 64) {
+        const uint32_t i = lds_u16(ord1_a + 2 * j);
+        const uint32_t e = lds_u16(rp_a + 2 * i), e1 = lds_u16(rp_a + 2 * i + 2);
+        sts_f4(t1s_q + i * 128, gather_row(ent_a, e, e1, xs_q));
       }
+      producer_barrier();
+      // (2) T2 = 2 L~ T1 - X on the tile rows (a tile row's neighbours all have a T1 slot)
+      float4 t0[2], t1[2], t2[2];
+      {
+        const float4 g0 = gather_row(ent_a, lds_u16(rp_a + 2 * row0), lds_u16(rp_a + 2 * row0 + 2), t1s_q);
+        const float4 g1 = gather_row(ent_a, lds_u16(rp_a + 2 * row1), lds_u16(rp_a + 2 * row1 + 2), t1s_q);
+        t0[0] = lds_f4(xs_q + row0 * 128);
+        t0[1] = lds_f4(xs_q + row1 * 128);
+        t1[0] = lds_f4(t1s_q + row0 * 128);
+        t1[1] = lds_f4(t1s_q + row1 * 128);
+        t2[0] = make_float4(2.f * g0.x - t0[0].x, 2.f * g0.y - t0[0].y, 2.f * g0.z - t0[0].z, 2.f * g0.w - t0[0].w);
+        t2[1] = make_float4(2.f * g1.x - t0[1].x, 2.f * g1.y - t0[1].y, 2.f * g1.z - t0[1].z, 2.f * g1.w - t0[1].w);
+      }
+      // (3) split to fp16 (hi, lo) and write the three K-blocks into the A/B ring
+#pragma unroll
+      for (int k = 0; k < 3; ++k, ++ucnt) {
+        const int s = ucnt % NS;
+        mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
+        const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const uint32_t i = ps ? row1 : row0;
+          const float4 v = (k == 0) ? t0[ps] : (k == 1 ? t1[ps] : t2[ps]);
+          uint2 hi, lo;
+          split4(v, hi, lo);
+          sts_u2(ablk + sw128_off(i, q >> 1), hi);
+          sts_u2(ablk + sw128_off(i, 4 + (q >> 1)), lo);
+        }
+        fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(smem_u32(b_ab_full + s));
+      }
+      producer_barrier();  // everybody is done with Xs[xs] and T1s
+      if (XS == 1 && g + 1 < n_stage) issue_halo_loads(g + 1);  // single X stage: no overlap possible
+      if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
     }
   }
   tc_fence_before();
