@@ -104,6 +104,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
   *abort_flag = 1;
   atomicExch(status, code);
 }
+// Same, but with a nanosleep back-off between polls: for the roles whose waits span most of a tile
+// (epilogue, loaders) so that their polling does not steal issue slots from the producers.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status,
+                                                  int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int it = 0; it < 16; ++it) {
+      if (mbar_try_wait(bar, parity)) return;
+      __nanosleep(200);
+    }
+    if (*abort_flag) return;
+    if (global_ns() - t0 > 400000000ull) break;
+  }
+  *abort_flag = 1;
+  atomicExch(status, code);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -152,6 +170,41 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.y = fmaf(w, x.y, acc.y);
   acc.z = fmaf(w, x.z, acc.z);
   acc.w = fmaf(w, x.w, acc.w);
+}
+// Two independent rows at once (twice the loads in flight per thread); ranges packed as lo16 = begin, hi16 = end.
+__device__ __forceinline__ void gather_rows2(uint32_t ent, uint32_t ra, uint32_t rb, uint32_t rows_q, float4& accA,
+                                             float4& accB) {
+  uint32_t ea = ra & 0xFFFFu, ea1 = ra >> 16, eb = rb & 0xFFFFu, eb1 = rb >> 16;
+  accA = make_float4(0.f, 0.f, 0.f, 0.f);
+  accB = make_float4(0.f, 0.f, 0.f, 0.f);
+  while (ea < ea1 && eb < eb1) {
+    const uint2 a0 = lds_u2(ent + ea * 8), b0 = lds_u2(ent + eb * 8);
+    const float4 x0 = lds_f4(rows_q + a0.x), y0 = lds_f4(rows_q + b0.x);
+    fma4(accA, __uint_as_float(a0.y), x0);
+    fma4(accB, __uint_as_float(b0.y), y0);
+    ++ea;
+    ++eb;
+  }
+  for (; ea + 1 < ea1; ea += 2) {
+    const uint2 a0 = lds_u2(ent + ea * 8), a1 = lds_u2(ent + ea * 8 + 8);
+    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x);
+    fma4(accA, __uint_as_float(a0.y), x0);
+    fma4(accA, __uint_as_float(a1.y), x1);
+  }
+  if (ea < ea1) {
+    const uint2 a0 = lds_u2(ent + ea * 8);
+    fma4(accA, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
+  }
+  for (; eb + 1 < eb1; eb += 2) {
+    const uint2 b0 = lds_u2(ent + eb * 8), b1 = lds_u2(ent + eb * 8 + 8);
+    const float4 y0 = lds_f4(rows_q + b0.x), y1 = lds_f4(rows_q + b1.x);
+    fma4(accB, __uint_as_float(b0.y), y0);
+    fma4(accB, __uint_as_float(b1.y), y1);
+  }
+  if (eb < eb1) {
+    const uint2 b0 = lds_u2(ent + eb * 8);
+    fma4(accB, __uint_as_float(b0.y), lds_f4(rows_q + b0.x));
+  }
 }
 // acc += sum_e val[e] * rows[slot[e]][q]  over the CSR entries [e, e1) of one row; `rows` = staged X or T1
 __device__ __forceinline__ float4 gather_row(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
@@ -254,17 +307,26 @@ struct KParams {
   int res_identity;       // residual resampling is the identity (Fin_block == Fout): vector path
   float* y;
   int* status;
+  long long* trace;  // optional [8][512] event log of CTA 0 (debug): (event << 48) | clock
 };
 
-// Warp roles (23 warps, one persistent CTA per SM):
+__device__ __forceinline__ void trace_ev(const KParams& p, int role, int& n, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && n < 512) {
+    p.trace[role * 512 + n] = ((long long)ev << 48) | (clock64() & 0xFFFFFFFFFFFFll);
+    ++n;
+  }
+}
+
+// Warp roles (24 warps, one persistent CTA per SM):
 //   0..15  producers: SpMM out of shared memory + fp16 (hi,lo) split + swizzled A-block stores
-//   16     halo loader: per (tile, chunk) one cp.async.bulk per staged X row, per tile the metadata blob
-//   17     weight-block loader (one thread, cp.async.bulk)
-//   18     MMA issuer (one thread) and TMEM owner
-//   19..22 epilogue: TMEM -> registers -> fused epilogue -> HBM, overlapped with the next tile's main loop
+//   16,17  halo loaders: per (tile, chunk) stage the 2-hop halo rows of X with 16-byte cp.async copies
+//          (completion: cp.async.mbarrier.arrive.noinc); thread 0 also fetches the tile metadata (cp.async.bulk)
+//   18     weight-block loader (one thread, cp.async.bulk)
+//   19     MMA issuer (one thread) and TMEM owner
+//   20..23 epilogue: TMEM -> registers -> fused epilogue -> HBM, overlapped with the next tile's main loop
 constexpr int W_PROD = 16;
-constexpr int W_XLOAD = 16, W_BLOAD = 17, W_MMA = 18, W_EPI0 = 19;
-constexpr int NUM_THREADS2 = 23 * 32;
+constexpr int W_XLOAD = 16, N_XLOAD = 2, W_BLOAD = 18, W_MMA = 19, W_EPI0 = 20;
+constexpr int NUM_THREADS2 = 24 * 32;
 
 template <int N, int NS, int XS>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParams p) {
@@ -291,6 +353,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
   uint64_t* b_acc_empty = b_acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_acc_empty + 2);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* ep_mul = reinterpret_cast<float*>(tmem_slot + 4);  // [N] acc * mul + add  (weight scale, bias, folded BN)
+  float* ep_add = ep_mul + N;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -300,12 +364,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(b_ab_full + s), W_PROD * 32 + 1);
+      mbar_init(smem_u32(b_ab_full + s), W_PROD + 1);  // one elected arrive per producer warp + the weight loader
       mbar_init(smem_u32(b_ab_empty + s), 1);
     }
     for (int s = 0; s < XS; ++s) {
-      mbar_init(smem_u32(b_x_full + s), W_PROD * 32);  // every producer thread: cp.async.mbarrier.arrive.noinc
-      mbar_init(smem_u32(b_x_empty + s), 1);           // (unused: the producers are also the consumers)
+      mbar_init(smem_u32(b_x_full + s), N_XLOAD * 32);  // every loader thread: cp.async.mbarrier.arrive.noinc
+      mbar_init(smem_u32(b_x_empty + s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(b_m_full + s), 1);
@@ -317,35 +381,75 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     if (*abort_flag) atomicExch(p.status, 100);
     fence_barrier_init();
   }
+  for (int n = threadIdx.x; n < N; n += NUM_THREADS2) {
+    const float sc = p.ep.scale ? p.ep.scale[n] : 1.f;
+    const float sh = p.ep.scale ? p.ep.shift[n] : 0.f;
+    const float bi = p.ep.bias ? p.ep.bias[n] : 0.f;
+    ep_mul[n] = W_INV_SCALE * sc;
+    ep_add[n] = fmaf(bi, sc, sh);
+  }
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == W_XLOAD) {
-    // ------------------------------------------------------------ tile-metadata loader (one thread, cp.async.bulk)
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int pat = tile % p.P;
-        const int m = it & 1;
-        mbar_wait(smem_u32(b_m_empty + m), ((it >> 1) & 1) ^ 1, abort_flag, p.status, 1);
-        const int mbytes = p.meta_bytes[pat];
-        mbar_arrive_expect_tx(smem_u32(b_m_full + m), mbytes);
-        bulk_g2s(smem_u32(meta_s + (size_t)m * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
-                 smem_u32(b_m_full + m));
+  if (warp >= W_XLOAD && warp < W_XLOAD + N_XLOAD) {
+    // ------------------------------------------------------------ halo loaders (2 warps) + tile metadata
+    const int lt = tid - W_XLOAD * 32;   // 0..63
+    const int q = lt & 7, rg = lt >> 3;   // 8 lanes x 16 B per 128-byte row, 8 rows per pass
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto fetch_meta = [&](int it2) {      // one thread: cp.async.bulk of the tile's metadata blob
+      const int pat = (blockIdx.x + it2 * gridDim.x) % p.P;
+      const int m2 = it2 & 1;
+      mbar_wait_relaxed(smem_u32(b_m_empty + m2), ((it2 >> 1) & 1) ^ 1, abort_flag, p.status, 1);
+      const int mbytes = p.meta_bytes[pat];
+      mbar_arrive_expect_tx(smem_u32(b_m_full + m2), mbytes);
+      bulk_g2s(smem_u32(meta_s + (size_t)m2 * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
+               smem_u32(b_m_full + m2));
+    };
+    if (lt == 0 && my_tiles > 0) fetch_meta(0);
+    uint32_t g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / p.P;
+      const int m = it & 1;
+      mbar_wait_relaxed(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 2);
+      const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
+      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
+      const int h2 = hdr->h2;
+      const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);
+      const long long mesh_row0 = (long long)b * p.V;
+      for (int c = 0; c < n_chunk; ++c, ++g) {
+        const int xs = g % XS;
+        mbar_wait_relaxed(smem_u32(b_x_empty + xs), ((g / XS) & 1) ^ 1, abort_flag, p.status, 3);
+        const uint32_t dst0 = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
+        const float* src0 = p.x + c * FC + q * 4;
+        for (int i = rg; i < h2; i += 8) {
+          const int v = halo[i];
+          if (v >= 0) {
+            long long r = mesh_row0 + v;
+            if (p.in_unpool) r >>= 1;
+            cp_async16(dst0 + i * 128, src0 + r * p.fin);
+          } else {
+            sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+        cp_async_arrive_noinc(smem_u32(b_x_full + xs));
+        if (c == 0 && lt == 0 && it + 1 < my_tiles) fetch_meta(it + 1);  // overlaps this tile's main loop
       }
     }
   } else if (warp == W_BLOAD) {
     // ------------------------------------------------------------ weight-block loader (one thread)
     if (lane == 0) {
       uint32_t ucnt = 0;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int u = 0; u < n_use; ++u, ++ucnt) {
           const int s = ucnt % NS;
           const uint32_t par = (ucnt / NS) & 1;
-          mbar_wait(smem_u32(b_ab_empty + s), par ^ 1, abort_flag, p.status, 4);
+          mbar_wait_relaxed(smem_u32(b_ab_empty + s), par ^ 1, abort_flag, p.status, 4);
+          trace_ev(p, 1, tn, 10 + u);
           mbar_arrive_expect_tx(smem_u32(b_ab_full + s), B_BLOCK_BYTES);
           bulk_g2s(smem_u32(ring + s * SLOT_BYTES + A_BLOCK_BYTES), p.wpack + (size_t)u * B_BLOCK_BYTES, B_BLOCK_BYTES,
                    smem_u32(b_ab_full + s));
@@ -357,14 +461,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     if (lane == 0) {
       uint32_t ucnt = 0;
       int it = 0;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         mbar_wait(smem_u32(b_acc_empty + as), ((it >> 1) & 1) ^ 1, abort_flag, p.status, 5);
+        trace_ev(p, 2, tn, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
         for (int u = 0; u < n_use; ++u, ++ucnt) {
           const int s = ucnt % NS;
           mbar_wait(smem_u32(b_ab_full + s), (ucnt / NS) & 1, abort_flag, p.status, 6);
+          trace_ev(p, 2, tn, 10 + u);
           tc_fence_after();
           const uint32_t a0 = smem_u32(ring + s * SLOT_BYTES);
           const uint64_t da = make_desc_sw128(a0), db = make_desc_sw128(a0 + A_BLOCK_BYTES);
@@ -386,6 +493,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     const int lane_base = (warp & 3) * 32;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     const int row_in_tile = lane_base + lane;
     int it = 0;
+    int etn = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.P, pat = tile - b * p.P;
       const int as = it & 1;
@@ -395,7 +503,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       float* yrow = p.y + r * N;
       const float* res_row = nullptr;
       if (p.ep.res != nullptr) res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
-      mbar_wait(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
+      mbar_wait_relaxed(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
+      if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 1);
       tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < N; cb += 32) {
@@ -408,9 +517,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float t = __uint_as_float(v[j + e]) * W_INV_SCALE;
-              if (p.ep.bias) t += p.ep.bias[n + e];
-              if (p.ep.scale) t = fmaf(t, p.ep.scale[n + e], p.ep.shift[n + e]);
+              float t = fmaf(__uint_as_float(v[j + e]), ep_mul[n + e], ep_add[n + e]);
               if (p.ep.relu) t = fmaxf(t, 0.f);
               o[e] = t;
             }
@@ -432,6 +539,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 2);
       if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
     }
   } else {
@@ -444,73 +552,75 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     const int n_stage = my_tiles * n_chunk;  // flat sequence of (tile, chunk) stages of this CTA
     uint32_t ucnt = 0;
 
-    // Stage the 2-hop halo of X for flat stage g into Xs[g % XS] with 16-byte cp.async copies (8 lanes per
-    // 128-byte row); completion is signalled on x_full[g % XS] by cp.async.mbarrier.arrive.noinc.
-    auto issue_halo_loads = [&](int g) {
-      const int it2 = g / n_chunk, c2 = g - it2 * n_chunk;
-      const int tile2 = blockIdx.x + it2 * gridDim.x;
-      const int b2 = tile2 / p.P;
-      const int m2 = it2 & 1;
-      if (c2 == 0) mbar_wait(smem_u32(b_m_full + m2), (it2 >> 1) & 1, abort_flag, p.status, 8);
-      const unsigned char* mb2 = meta_s + (size_t)m2 * p.meta_stride;
-      const TileHeader* hdr2 = reinterpret_cast<const TileHeader*>(mb2);
-      const int h2 = hdr2->h2;
-      const int* halo = reinterpret_cast<const int*>(mb2 + hdr2->off_halo);
-      const long long mesh_row0 = (long long)b2 * p.V;
-      const int xs2 = g % XS;
-      const uint32_t dst0 = smem_u32(Xs + xs2 * xs_stage_floats) + q * 16;
-      const float* src0 = p.x + c2 * FC + q * 4;
-      for (int i = rg; i < h2; i += 64) {
-        const int v = halo[i];
-        if (v >= 0) {
-          long long r = mesh_row0 + v;
-          if (p.in_unpool) r >>= 1;
-          cp_async16(dst0 + i * 128, src0 + r * p.fin);
-        } else {
-          sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-      }
-      cp_async_arrive_noinc(smem_u32(b_x_full + xs2));
-    };
-
-    if (n_stage > 0) issue_halo_loads(0);
+    constexpr int T1_ROWS = 4;  // max_h1 <= 256 rows over 64 row groups (checked on the host)
+    uint32_t t1_row[T1_ROWS], t1_e[T1_ROWS];
+    uint32_t row0 = 0, row1 = 0, r0e = 0, r1e = 0, ent_a = 0;
+    int ptn = 0;
     for (int g = 0; g < n_stage; ++g) {
       const int it = g / n_chunk, c = g - it * n_chunk;
       const int m = it & 1;
-      if (XS == 2 && g + 1 < n_stage) issue_halo_loads(g + 1);  // prefetch: overlaps this stage's SpMM
       const int xs = g % XS;
+      if (c == 0) mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 8);
+      if (tid == 0) trace_ev(p, 0, ptn, 1);
       mbar_wait(smem_u32(b_x_full + xs), (g / XS) & 1, abort_flag, p.status, 9);
+      if (tid == 0) trace_ev(p, 0, ptn, 2);
 
-      const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
-      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
-      const int h1 = hdr->h1;
-      const uint32_t mb_a = smem_u32(mb);
-      const uint32_t rp_a = mb_a + hdr->off_rp, ent_a = mb_a + hdr->off_ent;
-      const uint32_t ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
-      // the two tile rows this thread finishes
-      const uint32_t row0 = lds_u16(ord2_a + 2 * rg), row1 = lds_u16(ord2_a + 2 * (64 + rg));
+      if (c == 0) {  // per-tile bookkeeping: which rows this thread owns and where their CSR rows start/end
+        const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
+        const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
+        const uint32_t mb_a = smem_u32(mb);
+        const uint32_t rp_a = mb_a + hdr->off_rp, ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
+        ent_a = mb_a + hdr->off_ent;
+        const int h1 = hdr->h1;
+#pragma unroll
+        for (int t = 0; t < T1_ROWS; ++t) {
+          const int j = rg + 64 * t;
+          t1_row[t] = 0xFFFFu;
+          if (j < h1) {
+            const uint32_t i = lds_u16(ord1_a + 2 * j);
+            t1_row[t] = i;
+            t1_e[t] = lds_u16(rp_a + 2 * i) | (lds_u16(rp_a + 2 * i + 2) << 16);
+          }
+        }
+        row0 = lds_u16(ord2_a + 2 * rg);
+        row1 = lds_u16(ord2_a + 2 * (64 + rg));
+        r0e = lds_u16(rp_a + 2 * row0) | (lds_u16(rp_a + 2 * row0 + 2) << 16);
+        r1e = lds_u16(rp_a + 2 * row1) | (lds_u16(rp_a + 2 * row1 + 2) << 16);
+      }
       const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
       const uint32_t t1s_q = t1s_a + q * 16;
-      // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows)
-      for (int j = rg; j < h1; j += 64) {
-        const uint32_t i = lds_u16(ord1_a + 2 * j);
-        const uint32_t e = lds_u16(rp_a + 2 * i), e1 = lds_u16(rp_a + 2 * i + 2);
-        sts_f4(t1s_q + i * 128, gather_row(ent_a, e, e1, xs_q));
+      // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows); two rows per
+      //     thread are gathered together for memory-level parallelism.
+#pragma unroll
+      for (int t = 0; t < T1_ROWS; t += 2) {
+        if (t1_row[t] != 0xFFFFu) {
+          float4 ga, gb;
+          gather_rows2(ent_a, t1_e[t], t1_row[t + 1] != 0xFFFFu ? t1_e[t + 1] : 0u, xs_q, ga, gb);
+          sts_f4(t1s_q + t1_row[t] * 128, ga);
+          if (t1_row[t + 1] != 0xFFFFu) sts_f4(t1s_q + t1_row[t + 1] * 128, gb);
+        }
       }
+      if (tid == 0) trace_ev(p, 0, ptn, 4);
       producer_barrier();
-      // (2) T2 = 2 L~ T1 - X on the tile rows (a tile row's neighbours all have a T1 slot)
-      float4 t0[2], t1[2], t2[2];
+      if (tid == 0) trace_ev(p, 0, ptn, 5);
+      // (2) T2 = 2 L~ T1 - X on the two tile rows this thread finishes
+      float4 tv[3][2];
       {
-        const float4 g0 = gather_row(ent_a, lds_u16(rp_a + 2 * row0), lds_u16(rp_a + 2 * row0 + 2), t1s_q);
-        const float4 g1 = gather_row(ent_a, lds_u16(rp_a + 2 * row1), lds_u16(rp_a + 2 * row1 + 2), t1s_q);
-        t0[0] = lds_f4(xs_q + row0 * 128);
-        t0[1] = lds_f4(xs_q + row1 * 128);
-        t1[0] = lds_f4(t1s_q + row0 * 128);
-        t1[1] = lds_f4(t1s_q + row1 * 128);
-        t2[0] = make_float4(2.f * g0.x - t0[0].x, 2.f * g0.y - t0[0].y, 2.f * g0.z - t0[0].z, 2.f * g0.w - t0[0].w);
-        t2[1] = make_float4(2.f * g1.x - t0[1].x, 2.f * g1.y - t0[1].y, 2.f * g1.z - t0[1].z, 2.f * g1.w - t0[1].w);
+        float4 g0, g1;
+        gather_rows2(ent_a, r0e, r1e, t1s_q, g0, g1);
+        tv[0][0] = lds_f4(xs_q + row0 * 128);
+        tv[0][1] = lds_f4(xs_q + row1 * 128);
+        tv[1][0] = lds_f4(t1s_q + row0 * 128);
+        tv[1][1] = lds_f4(t1s_q + row1 * 128);
+        const float4 a = tv[0][0], c2 = tv[0][1];
+        tv[2][0] = make_float4(2.f * g0.x - a.x, 2.f * g0.y - a.y, 2.f * g0.z - a.z, 2.f * g0.w - a.w);
+        tv[2][1] = make_float4(2.f * g1.x - c2.x, 2.f * g1.y - c2.y, 2.f * g1.z - c2.z, 2.f * g1.w - c2.w);
       }
-      // (3) split to fp16 (hi, lo) and write the three K-blocks into the A/B ring
+      if (tid == 0) trace_ev(p, 0, ptn, 6);
+      // (3) split to fp16 (hi, lo) and write the three K-blocks; ONE generic->async proxy fence for all of
+      //     them (the fence drains the thread's outstanding shared stores and is expensive).  Odd row groups
+      //     store lo first: a warp then covers both 64-byte halves of its rows per store (conflict-free).
+      const uint32_t u0 = ucnt;
 #pragma unroll
       for (int k = 0; k < 3; ++k, ++ucnt) {
         const int s = ucnt % NS;
@@ -519,18 +629,38 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           const uint32_t i = ps ? row1 : row0;
-          const float4 v = (k == 0) ? t0[ps] : (k == 1 ? t1[ps] : t2[ps]);
           uint2 hi, lo;
-          split4(v, hi, lo);
-          sts_u2(ablk + sw128_off(i, q >> 1), hi);
-          sts_u2(ablk + sw128_off(i, 4 + (q >> 1)), lo);
+          split4(tv[k][ps], hi, lo);
+          const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
+          if (rg & 1) {
+            sts_u2(a_lo, lo);
+            sts_u2(a_hi, hi);
+          } else {
+            sts_u2(a_hi, hi);
+            sts_u2(a_lo, lo);
+          }
         }
-        fence_async_proxy();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(smem_u32(b_ab_full + s));
+        if (NS < 3) {  // ring shorter than a chunk: the third block re-uses the first block's slot -> publish each
+          fence_async_proxy();
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
+        }
       }
+      if (NS >= 3) {
+        fence_async_proxy();
+        __syncwarp();
+        if ((tid & 31) == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) mbar_arrive(smem_u32(b_ab_full + (u0 + k) % NS));  // one arrival per warp
+        }
+      }
+      if (tid == 0) trace_ev(p, 0, ptn, 7);
       producer_barrier();  // everybody is done with Xs[xs] and T1s
-      if (XS == 1 && g + 1 < n_stage) issue_halo_loads(g + 1);  // single X stage: no overlap possible
-      if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+      if (tid == 0) trace_ev(p, 0, ptn, 8);
+      if (tid == 0) {
+        mbar_arrive(smem_u32(b_x_empty + xs));
+        if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+      }
     }
   }
   tc_fence_before();
@@ -562,9 +692,11 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
   *reinterpret_cast<uint4*>(out + (size_t)u * fout * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
 }
 
+long long* g_umma_trace = nullptr;  // debug: set through set_umma_trace()
+
 size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g) {
   return 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +
-         2 * (size_t)g.meta_stride + 8 * (2 * NS + 2 * XS + 8) + 16;
+         2 * (size_t)g.meta_stride + 8 * (2 * NS + 2 * XS + 8) + 16 + 2 * (size_t)N * 4 + 16;
 }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 inline int ring_stages(int N) { return N == 256 ? 2 : 3; }
@@ -597,6 +729,7 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.res_identity = (a.ep.res != nullptr && a.ep.res_F == a.fout) ? 1 : 0;
   p.y = a.y;
   p.status = status;
+  p.trace = g_umma_trace;
   const int grid = std::min(p.n_tiles, sm_count);
   kern<<<grid, NUM_THREADS2, smem, s>>>(p);
   P2M_LAUNCH_OK();
@@ -724,9 +857,12 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
   return P2M_OK;
 }
 
+void set_umma_trace(long long* dev_buf) { g_umma_trace = dev_buf; }
+
 bool umma_conv_supported(const DevLevel& g, int fin, int fout) {
   if (g.tile_meta == nullptr || g.n_pattern <= 0) return false;
   if (fin % FC != 0 || fin < FC || fin > 256) return false;
+  if (g.max_h1 > 256) return false;  // producers keep <= 4 T1 rows per row group
   if (fout != 64 && fout != 128 && fout != 256) return false;
   return smem_bytes_for(fout, ring_stages(fout), 1, g) <= SMEM_LIMIT;
 }

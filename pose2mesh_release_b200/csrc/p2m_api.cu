@@ -453,6 +453,12 @@ int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out) {
   return P2M_OK;
 }
 
+// Debug: route the tcgen05 kernel's CTA-0 event log into `dev_buf` (device, 8*512 int64) or disable (NULL).
+int p2m_debug_set_trace(void* dev_buf) {
+  set_umma_trace(static_cast<long long*>(dev_buf));
+  return P2M_OK;
+}
+
 int p2m_model_set_profiling(p2m_model_t* m, int enable) {
   if (!m) {
     set_error("set_profiling: bad argument");
