@@ -69,25 +69,34 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        """Launch the sampler (nvidia-smi needs ~1 s to print its first line) and wait for the first sample."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        self.t_begin = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.time()
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if getattr(self, "t_begin", 0) - 0.05 <= t <= t_end + 0.12]
+        for ln in (inside or [ln for (_, ln) in self.lines[-3:]]):
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -286,6 +295,7 @@ def main():
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     lib.p2m_launch_count_reset()
     barrier()
+    sampler.mark()
     for i in range(args.steps):
         flush.zero_()               # evict L2 between timed iterations (not timed)
         evs[i][0].record()
