@@ -204,11 +204,33 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "meshes/s", "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
                              "sample": f"{steps} x {sample} meshes, eval forward, CPU oracle (torch CPU kernels)"},
             "e2e": {"value": v, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract goes to the real stdout; everything libraries print (NCCL's version
+    banner, torch warnings) was diverted to stderr by capture_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -225,6 +247,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -416,7 +440,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "gpu_launches_per_step": int(per_step_launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "layers": layers,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
