@@ -101,6 +101,14 @@ size_t p2m_meshnet_backward_scratch_bytes(const p2m_model_t* m, int batch);
 int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* params, const float* x, float* y, int batch,
                         int training, void* workspace, size_t workspace_bytes, p2m_stream_t stream);
 
+/* Fused output gather: the callers' `pred[:, perm_reverse[:n_real], :]`
+ * (lib/core/base.py:130,201; demo/run.py:170) folded into the head layer's store.  `vertex_of_slot` (HOST,
+ * int32[n_slots]) is perm_reverse[:n_real]; p2m_meshnet_forward_vertices then writes y_vertices [B, n_slots, Cout]
+ * (eval mode) instead of the padded [B, V0, Cout].                                                    */
+int p2m_model_set_output_gather(p2m_model_t* m, const int32_t* vertex_of_slot, int n_slots);
+int p2m_meshnet_forward_vertices(p2m_model_t* m, const p2m_params_t* params, const float* x, float* y_vertices,
+                                 int batch, void* workspace, size_t workspace_bytes, p2m_stream_t stream);
+
 /* Backward of the training forward above.  dy [B,V0,Cout]; dx [B,J,Cin] (may be NULL).  Gradients
  * are WRITTEN (not accumulated) into `grads`.                                                     */
 int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* params, const p2m_params_t* grads, const float* x,

@@ -73,7 +73,7 @@ class ConvBwdArgs(C.Structure):
 EXPORTS = [
     "p2m_model_create", "p2m_model_destroy", "p2m_model_num_layers", "p2m_model_layer_info",
     "p2m_model_set_precision", "p2m_debug_kernel_status", "p2m_debug_set_trace", "p2m_model_set_profiling", "p2m_model_layer_times_ms", "p2m_meshnet_workspace_bytes", "p2m_meshnet_backward_scratch_bytes",
-    "p2m_meshnet_forward", "p2m_meshnet_backward", "p2m_meshnet_host_io_bytes", "p2m_meshnet_forward_host",
+    "p2m_meshnet_forward", "p2m_meshnet_backward", "p2m_model_set_output_gather", "p2m_meshnet_forward_vertices", "p2m_meshnet_host_io_bytes", "p2m_meshnet_forward_host",
     "p2m_cheb_conv_workspace_bytes", "p2m_cheb_conv_fwd", "p2m_cheb_conv_bwd", "p2m_graph_match_level",
     "p2m_last_error", "p2m_version", "p2m_launch_count", "p2m_launch_count_reset",
 ]
@@ -122,6 +122,10 @@ def load() -> C.CDLL:
         lib.p2m_meshnet_host_io_bytes.restype = sz
         lib.p2m_meshnet_forward.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, C.c_int, vp, sz, vp]
         lib.p2m_meshnet_forward.restype = C.c_int
+        lib.p2m_model_set_output_gather.argtypes = [vp, c_int32_p, C.c_int]
+        lib.p2m_model_set_output_gather.restype = C.c_int
+        lib.p2m_meshnet_forward_vertices.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, vp, sz, vp]
+        lib.p2m_meshnet_forward_vertices.restype = C.c_int
         lib.p2m_meshnet_forward_host.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, vp, sz, vp]
         lib.p2m_meshnet_forward_host.restype = C.c_int
         lib.p2m_meshnet_backward.argtypes = [vp, C.POINTER(Params), C.POINTER(Params), vp, vp, vp, C.c_int, vp, sz,

@@ -428,7 +428,13 @@ __global__ void __launch_bounds__(256) k_thin_out(const int* __restrict__ rowptr
     acc.x = fmaf(w, u.x, acc.x); acc.y = fmaf(w, u.y, acc.y); acc.z = fmaf(w, u.z, acc.z); acc.w = fmaf(w, u.w, acc.w);
   }
   const float o[4] = {acc.x, acc.y, acc.z, acc.w};
-  for (int n = 0; n < fout; ++n) y[r * fout + n] = apply_epilogue(o[n], r, n, ep);
+  long long ro = r;
+  if (ep.out_map != nullptr) {  // fused perm_reverse gather: keep only the real vertices, in mesh order
+    const int slot = ep.out_map[v];
+    if (slot < 0) return;
+    ro = (r / V) * ep.out_rows + slot;
+  }
+  for (int n = 0; n < fout; ++n) y[ro * fout + n] = apply_epilogue(o[n], r, n, ep);
 }
 
 bool thin_conv_supported(int fin, int fout) { return fout <= 4 && (fin == 64 || fin == 32); }

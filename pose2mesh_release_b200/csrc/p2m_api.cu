@@ -48,6 +48,8 @@ struct p2m_model {
   int n_joint = 0, cin = 0, cout = 0;
   int fc_in = 0, fc_out = 0;
   int* kernel_status = nullptr;  // device word set by a tcgen05 kernel whose mbarrier wait timed out
+  int* out_map = nullptr;        // optional fused output gather (vertex -> slot, -1 = dropped)
+  int out_rows = 0;
   float* zero_row = nullptr;     // 128 B of zeros (halo source for the empty slots of ragged tiles)
   int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
   std::vector<cudaEvent_t> ev_beg, ev_end;
@@ -513,8 +515,8 @@ size_t p2m_meshnet_host_io_bytes(const p2m_model_t* m, int batch) {
 }
 
 // -------------------------------------------------------------------------------------
-int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, float* y, int B, int training,
-                        void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const float* x, float* y, int B, int training,
+                                void* workspace, size_t workspace_bytes, p2m_stream_t stream, int gathered) {
   if (!m || !x || !y || B <= 0 || !workspace || m->layers.empty()) {
     set_error("meshnet_forward: bad argument");
     return P2M_ERR_INVALID;
@@ -568,6 +570,15 @@ int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, f
         int out_buf = -1;
         if (last) {
           out = y;
+          if (gathered) {
+            if (!thin_conv_supported(L.fin, L.fout) || with_res) {
+              set_error("meshnet_forward_vertices: the head layer is not on the fused-gather path");
+              return P2M_ERR_INVALID;
+            }
+            ep.out_map = m->out_map;
+            ep.out_rows = m->out_rows;
+            ep.level_V = L.V;
+          }
         } else {
           for (int c = 0; c < 3; ++c)
             if (c != cur_buf && c != block_in_buf) {
@@ -625,6 +636,41 @@ int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, f
     }
   }
   return P2M_OK;
+}
+
+int p2m_meshnet_forward(p2m_model_t* m, const p2m_params_t* P, const float* x, float* y, int B, int training,
+                        void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  return meshnet_forward_impl(m, P, x, y, B, training, workspace, workspace_bytes, stream, 0);
+}
+
+int p2m_model_set_output_gather(p2m_model_t* m, const int32_t* vertex_of_slot, int n_slots) {
+  if (!m || m->layers.empty() || !vertex_of_slot || n_slots <= 0 || n_slots > m->levels[0].V) {
+    set_error("set_output_gather: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  const int V0 = m->levels[0].V;
+  std::vector<int> map(V0, -1);
+  for (int j = 0; j < n_slots; ++j) {
+    const int v = vertex_of_slot[j];
+    if (v < 0 || v >= V0 || map[v] >= 0) {
+      set_error("set_output_gather: index out of range or repeated");
+      return P2M_ERR_INVALID;
+    }
+    map[v] = j;
+  }
+  P2M_CUDA_OK(cudaSetDevice(m->device));
+  P2M_TRY(upload(m, map, &m->out_map));
+  m->out_rows = n_slots;
+  return P2M_OK;
+}
+
+int p2m_meshnet_forward_vertices(p2m_model_t* m, const p2m_params_t* P, const float* x, float* y_vertices, int B,
+                                 void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  if (!m || !m->out_map) {
+    set_error("meshnet_forward_vertices: call p2m_model_set_output_gather first");
+    return P2M_ERR_INVALID;
+  }
+  return meshnet_forward_impl(m, P, x, y_vertices, B, 0, workspace, workspace_bytes, stream, 1);
 }
 
 int p2m_meshnet_forward_host(p2m_model_t* m, const p2m_params_t* P, const float* x_host, float* y_host, int B,

@@ -87,6 +87,11 @@ struct Epilogue {
   const int* res_i0 = nullptr;
   const int* res_i1 = nullptr;
   const float* res_lam = nullptr;
+  // optional fused output gather (the callers' pred[:, perm_reverse[:n_real]], lib/core/base.py:130): row v of a
+  // mesh is stored at slot out_map[v] of a [B, out_rows, N] tensor, or dropped when out_map[v] < 0
+  const int* out_map = nullptr;
+  int out_rows = 0;
+  int level_V = 0;
 };
 #ifdef __CUDACC__
 // Device-side view of Epilogue + the per-element epilogue shared by the SIMT GEMM and the tcgen05 conv.
@@ -101,9 +106,13 @@ struct EpiDev {
   const int* i0;
   const int* i1;
   const float* lam;
+  const int* out_map;
+  int out_rows;
+  int level_V;
 };
 inline EpiDev to_dev(const Epilogue& e) {
-  return EpiDev{e.bias, e.scale, e.shift, e.relu, e.res, e.res_F, e.res_unpool, e.res_i0, e.res_i1, e.res_lam};
+  return EpiDev{e.bias, e.scale, e.shift, e.relu, e.res, e.res_F, e.res_unpool, e.res_i0, e.res_i1, e.res_lam,
+                e.out_map, e.out_rows, e.level_V};
 }
 __device__ __forceinline__ float apply_epilogue(float v, long long r, int n, const EpiDev& ep) {
   if (ep.bias) v += ep.bias[n];

@@ -307,6 +307,44 @@ class Pose2Mesh(nn.Module):
                 raise RuntimeError("parameters and input live on different devices")
         return _MeshNetFunction.apply(x, self._hier, self.training, self._bn_buffers(), n, *params)
 
+    @torch.no_grad()
+    def forward_vertices(self, x: torch.Tensor, perm_reverse, n_vertex: int) -> torch.Tensor:
+        """Eval forward with the callers' gather fused into the head layer's store:
+        equals ``self(x)[:, perm_reverse[:n_vertex], :]`` (lib/core/base.py:130,201; demo/run.py:170)
+        without materialising the padded ``[B, V0, 3]`` tensor.  Returns ``[B, n_vertex, 3]``."""
+        lib = _lib.load()
+        if self.training:
+            raise RuntimeError("forward_vertices is an inference entry point: call .eval() first")
+        n_joint = self.graph_L[-1].shape[0]
+        x = x.view(-1, n_joint, self.num_joint_input_chan)
+        if not x.is_cuda:
+            raise RuntimeError("pose2mesh_release_b200 runs on CUDA (sm_100a) only; got a CPU tensor")
+        x = x.contiguous().float()
+        dev = x.device
+        h = self._hier.handle(dev.index)
+        key = (dev.index, int(n_vertex))
+        if getattr(self, "_gather_key", None) != key:
+            idx = np.ascontiguousarray(np.asarray(perm_reverse)[:n_vertex], dtype=np.int32)
+            _lib.check(lib.p2m_model_set_output_gather(h, idx.ctypes.data_as(_lib.c_int32_p), int(n_vertex)),
+                       "p2m_model_set_output_gather")
+            self._gather_key = key
+        B = x.shape[0]
+        y = torch.empty((B, int(n_vertex), self.num_mesh_output_chan), device=dev, dtype=torch.float32)
+        ws_bytes = lib.p2m_meshnet_workspace_bytes(h, B, 0)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        n, params = self._flat_params()
+        n_bn = n - 1
+        rm, rv, nbt = self._bn_buffers()
+        table = _param_table(params[0], params[1], params[2:2 + n], params[2 + n:2 + 2 * n],
+                             list(params[2 + 2 * n:2 + 2 * n + n_bn]) + [None],
+                             list(params[2 + 2 * n + n_bn:]) + [None], rm, rv, nbt)
+        with torch.cuda.device(dev):
+            _lib.check(lib.p2m_meshnet_forward_vertices(h, C.byref(table), x.data_ptr(), y.data_ptr(), B,
+                                                        ws.data_ptr(), ws_bytes,
+                                                        torch.cuda.current_stream(dev).cuda_stream),
+                       "p2m_meshnet_forward_vertices")
+        return y
+
     def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
         """Inference with HOST tensors through p2m_meshnet_forward_host: H2D of the poses, the eval
         forward, D2H of the mesh, synchronised.  Used by bench.py's end-to-end figure."""

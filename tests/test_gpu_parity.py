@@ -315,3 +315,20 @@ def test_tcgen05_conv_matches_oracle(case):
     yo = mo.cheb_conv(x, lap, w, bias)
     err = rel_err(y, yo)
     assert err < 1e-5, err
+
+
+def test_fused_output_gather_matches_indexing():
+    """Row a9 of SURVEY.md §8: pred[:, perm_reverse[:n_real]] fused into the head layer's store."""
+    from pose2mesh_release_b200 import graph as pg
+
+    model, mats, mano = make_model("smpl_small", "fp16x3")
+    z, _ = graph_from_fixture("smpl_small")[1], None
+    perm_rev = np.asarray(load_npz("graph_smpl_small.npz")["perm_reverse"])
+    n_real = 1200
+    model.eval()
+    x = torch.randn(3, 17, 5, device=dev())
+    with torch.no_grad():
+        full = model(x)
+        picked = model.forward_vertices(x, perm_rev, n_real)
+    assert picked.shape == (3, n_real, 3)
+    assert torch.equal(picked, full[:, torch.as_tensor(perm_rev[:n_real], device=dev()), :])
