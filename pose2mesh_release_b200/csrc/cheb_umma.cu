@@ -171,40 +171,33 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.z = fmaf(w, x.z, acc.z);
   acc.w = fmaf(w, x.w, acc.w);
 }
-// Two independent rows at once (twice the loads in flight per thread); ranges packed as lo16 = begin, hi16 = end.
-__device__ __forceinline__ void gather_rows2(uint32_t ent, uint32_t ra, uint32_t rb, uint32_t rows_q, float4& accA,
-                                             float4& accB) {
-  uint32_t ea = ra & 0xFFFFu, ea1 = ra >> 16, eb = rb & 0xFFFFu, eb1 = rb >> 16;
-  accA = make_float4(0.f, 0.f, 0.f, 0.f);
-  accB = make_float4(0.f, 0.f, 0.f, 0.f);
-  while (ea < ea1 && eb < eb1) {
-    const uint2 a0 = lds_u2(ent + ea * 8), b0 = lds_u2(ent + eb * 8);
-    const float4 x0 = lds_f4(rows_q + a0.x), y0 = lds_f4(rows_q + b0.x);
-    fma4(accA, __uint_as_float(a0.y), x0);
-    fma4(accB, __uint_as_float(b0.y), y0);
-    ++ea;
-    ++eb;
+// One CSR row with four entries in flight: the four (slot, value) pairs are fetched first, then the four
+// 16-byte row pieces, then the FMAs on two accumulators — the row's dependent chain is ~2 shared-memory round
+// trips per four entries instead of two per entry (rows have <= 14 entries).
+__device__ __forceinline__ float4 gather_row4(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  for (; e + 3 < e1; e += 4) {
+    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8), a2 = lds_u2(ent + e * 8 + 16),
+                a3 = lds_u2(ent + e * 8 + 24);
+    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x), x2 = lds_f4(rows_q + a2.x),
+                 x3 = lds_f4(rows_q + a3.x);
+    fma4(acc0, __uint_as_float(a0.y), x0);
+    fma4(acc1, __uint_as_float(a1.y), x1);
+    fma4(acc0, __uint_as_float(a2.y), x2);
+    fma4(acc1, __uint_as_float(a3.y), x3);
   }
-  for (; ea + 1 < ea1; ea += 2) {
-    const uint2 a0 = lds_u2(ent + ea * 8), a1 = lds_u2(ent + ea * 8 + 8);
+  if (e + 1 < e1) {
+    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8);
     const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x);
-    fma4(accA, __uint_as_float(a0.y), x0);
-    fma4(accA, __uint_as_float(a1.y), x1);
+    fma4(acc0, __uint_as_float(a0.y), x0);
+    fma4(acc1, __uint_as_float(a1.y), x1);
+    e += 2;
   }
-  if (ea < ea1) {
-    const uint2 a0 = lds_u2(ent + ea * 8);
-    fma4(accA, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
+  if (e < e1) {
+    const uint2 a0 = lds_u2(ent + e * 8);
+    fma4(acc0, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
   }
-  for (; eb + 1 < eb1; eb += 2) {
-    const uint2 b0 = lds_u2(ent + eb * 8), b1 = lds_u2(ent + eb * 8 + 8);
-    const float4 y0 = lds_f4(rows_q + b0.x), y1 = lds_f4(rows_q + b1.x);
-    fma4(accB, __uint_as_float(b0.y), y0);
-    fma4(accB, __uint_as_float(b1.y), y1);
-  }
-  if (eb < eb1) {
-    const uint2 b0 = lds_u2(ent + eb * 8);
-    fma4(accB, __uint_as_float(b0.y), lds_f4(rows_q + b0.x));
-  }
+  return make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
 }
 // acc += sum_e val[e] * rows[slot[e]][q]  over the CSR entries [e, e1) of one row; `rows` = staged X or T1
 __device__ __forceinline__ float4 gather_row(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
@@ -592,13 +585,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows); two rows per
       //     thread are gathered together for memory-level parallelism.
 #pragma unroll
-      for (int t = 0; t < T1_ROWS; t += 2) {
-        if (t1_row[t] != 0xFFFFu) {
-          float4 ga, gb;
-          gather_rows2(ent_a, t1_e[t], t1_row[t + 1] != 0xFFFFu ? t1_e[t + 1] : 0u, xs_q, ga, gb);
-          sts_f4(t1s_q + t1_row[t] * 128, ga);
-          if (t1_row[t + 1] != 0xFFFFu) sts_f4(t1s_q + t1_row[t + 1] * 128, gb);
-        }
+      for (int t = 0; t < T1_ROWS; ++t) {
+        if (t1_row[t] != 0xFFFFu)
+          sts_f4(t1s_q + t1_row[t] * 128, gather_row4(ent_a, t1_e[t] & 0xFFFFu, t1_e[t] >> 16, xs_q));
       }
       if (tid == 0) trace_ev(p, 0, ptn, 4);
       producer_barrier();
@@ -606,8 +595,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       // (2) T2 = 2 L~ T1 - X on the two tile rows this thread finishes
       float4 tv[3][2];
       {
-        float4 g0, g1;
-        gather_rows2(ent_a, r0e, r1e, t1s_q, g0, g1);
+        const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
+        const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
         tv[0][0] = lds_f4(xs_q + row0 * 128);
         tv[0][1] = lds_f4(xs_q + row1 * 128);
         tv[1][0] = lds_f4(t1s_q + row0 * 128);
