@@ -298,6 +298,11 @@ struct KParams {
   const float* zero_row;  // 128 bytes of zeros: source of the empty halo slots of ragged tiles
   EpiDev ep;
   int res_identity;       // residual resampling is the identity (Fin_block == Fout): vector path
+  int plain;              // 1: plain GEMM y = x * B^T (no SpMM): one K-block per chunk, rows = the tile's own
+  const float* a_scale;   // optional device scalar: x is multiplied by it before the fp16 split (power of two,
+                          // chosen from max|x|: gradients are far below fp16's range) and divided out afterwards
+  long long ldy;          // row stride of y in floats, and first output column
+  int y_col0;
   float* y;
   int* status;
   long long* trace;  // optional [8][512] event log of CTA 0 (debug): (event << 48) | clock
@@ -374,12 +379,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     if (*abort_flag) atomicExch(p.status, 100);
     fence_barrier_init();
   }
+  const float a_scale = p.a_scale ? *p.a_scale : 1.f;
   for (int n = threadIdx.x; n < N; n += NUM_THREADS2) {
-    const float sc = p.ep.scale ? p.ep.scale[n] : 1.f;
+    const float sc = (p.ep.scale ? p.ep.scale[n] : 1.f) / a_scale;
     const float sh = p.ep.scale ? p.ep.shift[n] : 0.f;
     const float bi = p.ep.bias ? p.ep.bias[n] : 0.f;
     ep_mul[n] = W_INV_SCALE * sc;
-    ep_add[n] = fmaf(bi, sc, sh);
+    ep_add[n] = fmaf(bi, p.ep.scale ? p.ep.scale[n] : 1.f, sh);
   }
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       mbar_wait_relaxed(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 2);
       const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
       const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
-      const int h2 = hdr->h2;
+      const int h2 = p.plain ? TILE_M : hdr->h2;  // plain GEMM: only the tile's own rows are staged
       const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);
       const long long mesh_row0 = (long long)b * p.V;
       for (int c = 0; c < n_chunk; ++c, ++g) {
@@ -437,8 +443,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     if (lane == 0) {
       uint32_t ucnt = 0;
       int tn = 0;
+      const int uses = p.plain ? n_chunk : n_use;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int u = 0; u < n_use; ++u, ++ucnt) {
+        for (int u = 0; u < uses; ++u, ++ucnt) {
           const int s = ucnt % NS;
           const uint32_t par = (ucnt / NS) & 1;
           mbar_wait_relaxed(smem_u32(b_ab_empty + s), par ^ 1, abort_flag, p.status, 4);
@@ -461,7 +468,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
         trace_ev(p, 2, tn, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
-        for (int u = 0; u < n_use; ++u, ++ucnt) {
+        const int uses = p.plain ? n_chunk : n_use;
+        for (int u = 0; u < uses; ++u, ++ucnt) {
           const int s = ucnt % NS;
           mbar_wait(smem_u32(b_ab_full + s), (ucnt / NS) & 1, abort_flag, p.status, 6);
           trace_ev(p, 2, tn, 10 + u);
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       const int n_rows = min(TILE_M, p.V - pat * TILE_M);
       const long long r = (long long)b * p.V + (long long)pat * TILE_M + row_in_tile;
       const bool valid = row_in_tile < n_rows;
-      float* yrow = p.y + r * N;
+      float* yrow = p.y + r * p.ldy + p.y_col0;
       const float* res_row = nullptr;
       if (p.ep.res != nullptr) res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
       mbar_wait_relaxed(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
@@ -582,6 +590,33 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       }
       const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
       const uint32_t t1s_q = t1s_a + q * 16;
+      if (p.plain) {
+        // plain GEMM: the staged rows ARE the A operand (scaled into fp16 range if a_scale is given)
+        const int s = ucnt % NS;
+        mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
+        const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const uint32_t i = ps * 64 + rg;
+          float4 v = lds_f4(xs_q + i * 128);
+          v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
+          uint2 hi, lo;
+          split4(v, hi, lo);
+          const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
+          sts_u2(a_hi, hi);
+          sts_u2(a_lo, lo);
+        }
+        fence_async_proxy();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
+        ++ucnt;
+        producer_barrier();
+        if (tid == 0) {
+          mbar_arrive(smem_u32(b_x_empty + xs));
+          if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+        }
+        continue;
+      }
       // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows); two rows per
       //     thread are gathered together for memory-level parallelism.
 #pragma unroll
@@ -717,6 +752,10 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.ep = to_dev(a.ep);
   p.res_identity = (a.ep.res != nullptr && a.ep.res_F == a.fout) ? 1 : 0;
   p.y = a.y;
+  p.plain = a.plain;
+  p.a_scale = a.a_scale;
+  p.ldy = a.ldy > 0 ? a.ldy : a.fout;
+  p.y_col0 = a.y_col0;
   p.status = status;
   p.trace = g_umma_trace;
   const int grid = std::min(p.n_tiles, sm_count);
@@ -854,6 +893,34 @@ bool umma_conv_supported(const DevLevel& g, int fin, int fout) {
   if (g.max_h1 > 256) return false;  // producers keep <= 4 T1 rows per row group
   if (fout != 64 && fout != 128 && fout != 256) return false;
   return smem_bytes_for(fout, ring_stages(fout), 1, g) <= SMEM_LIMIT;
+}
+
+__global__ void __launch_bounds__(256) k_pack_plain(const float* __restrict__ Bmat, long long ld_n, long long ld_k, int N,
+                                                    int K, unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int total = (K / FC) * N * 8;
+  if (idx >= total) return;
+  const int j = idx & 7;
+  const int n = (idx >> 3) % N;
+  const int c = (idx >> 3) / N;
+  const int k0 = c * FC + (j & 3) * 8;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float w = Bmat[(long long)n * ld_n + (long long)(k0 + e) * ld_k] * W_SCALE;
+    const __half hi = __float2half_rn(w);
+    h[e] = (j < 4) ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)c * N * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
+}
+
+size_t umma_plain_pack_bytes(int N, int K) { return (size_t)(K / FC) * N * 128; }
+
+int launch_umma_pack_plain(const float* Bmat, long long ld_n, long long ld_k, int N, int K, void* wpack, cudaStream_t s) {
+  const int total = (K / FC) * N * 8;
+  k_pack_plain<<<(total + 255) / 256, 256, 0, s>>>(Bmat, ld_n, ld_k, N, K, static_cast<unsigned char*>(wpack));
+  P2M_LAUNCH_OK();
+  return P2M_OK;
 }
 
 size_t umma_wpack_bytes(int fin, int fout) { return (size_t)(fin / FC) * 3 * fout * 128; }

@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(256) k_basis_bwd_u(const int* __restrict__ row
   reinterpret_cast<vec*>(U)[r * fg + f] = fma4(1.f, d1, acc);
 }
 
-// scalar (per-feature) variant of the final combine: the transposed resampling stencil is per channel.
+// final combine: dXl = dT0 - dT2 + L~ U (+ resample^T(g_res)); VEC features per thread; pair-sum for the
+// virtual unpool (the physical row p receives logical rows 2p and 2p+1)
+template <int VEC>
 __global__ void __launch_bounds__(256) k_basis_bwd_dx(const int* __restrict__ rowptr, const int* __restrict__ reloff,
                                                       const float* __restrict__ val, int V, long long rows_out, int F,
                                                       const float* __restrict__ dT, const float* __restrict__ U,
@@ -147,30 +149,45 @@ __global__ void __launch_bounds__(256) k_basis_bwd_dx(const int* __restrict__ ro
                                                       const int* __restrict__ t_ptr, const int* __restrict__ t_idx,
                                                       const float* __restrict__ t_w, int pairsum,
                                                       float* __restrict__ dx) {
+  using vec = typename VecT<VEC>::type;
+  const int fg = F / VEC;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows_out * F) return;
-  long long ro = idx / F;
-  int f = (int)(idx - ro * F);
-  float total = 0.f;
+  if (idx >= rows_out * fg) return;
+  long long ro = idx / fg;
+  int f = (int)(idx - ro * fg);
+  float total[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) total[e] = 0.f;
   const int reps = pairsum ? 2 : 1;
+  const vec* Uv = reinterpret_cast<const vec*>(U);
+  const vec* Dv = reinterpret_cast<const vec*>(dT);
   for (int q = 0; q < reps; ++q) {
     long long r = pairsum ? (2 * ro + q) : ro;
     int v = (int)(r % V);
-    float acc = 0.f;
+    vec acc = zero_of(Uv[0]);
     int p0 = rowptr[v], p1 = rowptr[v + 1];
-    for (int p = p0; p < p1; ++p) acc = fmaf(val[p], U[(r + reloff[p]) * F + f], acc);
-    acc += dT[r * 3 * F + f] - dT[r * 3 * F + 2 * F + f];
-    if (g_res != nullptr) {
-      for (int p = t_ptr[f]; p < t_ptr[f + 1]; ++p) acc = fmaf(t_w[p], g_res[r * res_Fout + t_idx[p]], acc);
+    for (int p = p0; p < p1; ++p) acc = fma4(val[p], Uv[(r + reloff[p]) * fg + f], acc);
+    vec d0 = Dv[r * 3 * fg + f], d2 = Dv[r * 3 * fg + 2 * fg + f];
+    float a[VEC], b0[VEC], b2[VEC];
+    *reinterpret_cast<vec*>(a) = acc;
+    *reinterpret_cast<vec*>(b0) = d0;
+    *reinterpret_cast<vec*>(b2) = d2;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = a[e] + (b0[e] - b2[e]);
+      if (g_res != nullptr) {
+        const int fe = f * VEC + e;
+        for (int p = t_ptr[fe]; p < t_ptr[fe + 1]; ++p) t = fmaf(t_w[p], g_res[r * res_Fout + t_idx[p]], t);
+      }
+      total[e] += t;
     }
-    total += acc;
   }
-  dx[ro * F + f] = total;
+  *reinterpret_cast<vec*>(dx + (ro * fg + f) * VEC) = *reinterpret_cast<vec*>(total);
 }
 
 int launch_cheb_basis_bwd(const DevLevel& g, const float* dT, int rows, int F, float* U, const float* g_res,
                           int res_Fout, const InterpTable* it, int out_pairsum, float* dx, cudaStream_t s) {
-  const bool v4 = (F % 4 == 0);
+  const bool v4 = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
   long long n = (long long)rows * (v4 ? F / 4 : F);
   if (v4) {
     k_basis_bwd_u<4><<<cdiv(n, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, F, dT, U);
@@ -179,9 +196,16 @@ int launch_cheb_basis_bwd(const DevLevel& g, const float* dT, int rows, int F, f
   }
   P2M_LAUNCH_OK();
   long long rows_out = out_pairsum ? rows / 2 : rows;
-  k_basis_bwd_dx<<<cdiv(rows_out * F, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows_out, F, dT, U, g_res,
-                                                        res_Fout, it ? it->t_ptr : nullptr, it ? it->t_idx : nullptr,
-                                                        it ? it->t_w : nullptr, out_pairsum, dx);
+  if (v4)
+    k_basis_bwd_dx<4><<<cdiv(rows_out * F / 4, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows_out, F, dT, U,
+                                                                 g_res, res_Fout, it ? it->t_ptr : nullptr,
+                                                                 it ? it->t_idx : nullptr, it ? it->t_w : nullptr,
+                                                                 out_pairsum, dx);
+  else
+    k_basis_bwd_dx<1><<<cdiv(rows_out * F, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows_out, F, dT, U, g_res,
+                                                             res_Fout, it ? it->t_ptr : nullptr,
+                                                             it ? it->t_idx : nullptr, it ? it->t_w : nullptr,
+                                                             out_pairsum, dx);
   P2M_LAUNCH_OK();
   return P2M_OK;
 }
@@ -283,61 +307,77 @@ int launch_gemm(const float* A, int lda, const float* B, int ldb, int b_is_kn, f
   return P2M_OK;
 }
 
-// C[N1,N2] += A[M,N1]^T B[M,N2]; each CTA owns a 64x64 output tile and a chunk of M rows.
-constexpr int TN_CHUNK = 2048;
+// C[N1,N2] += A[M,N1]^T B[M,N2]; each CTA owns a 128x128 output tile and a chunk of M rows (8x8 register
+// tile per thread); partial sums are merged with fp32 atomics (C zeroed by the caller).
+constexpr int TN_CHUNK = 4096;
 __global__ void __launch_bounds__(256) k_gemm_tn_atomic(const float* __restrict__ A, int lda,
                                                         const float* __restrict__ B, int ldb, float* __restrict__ C,
-                                                        int ldc, int M, int N1, int N2) {
-  __shared__ __align__(16) float As[16][64 + 4];
-  __shared__ __align__(16) float Bs[16][64 + 4];
+                                                        int ldc, int M, int N1, int N2, int a_vec, int b_vec) {
+  __shared__ __align__(16) float As[16][128 + 4];
+  __shared__ __align__(16) float Bs[16][128 + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int a0 = blockIdx.y * 64, b0 = blockIdx.z * 64;
+  const int a0 = blockIdx.y * 128, b0 = blockIdx.z * 128;
   const long long mbeg = (long long)blockIdx.x * TN_CHUNK;
   const long long mend = min((long long)M, mbeg + TN_CHUNK);
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   for (long long m0 = mbeg; m0 < mend; m0 += 16) {
-    for (int e = tid; e < 16 * 64; e += 256) {
-      int k = e >> 6, n = e & 63;
-      long long m = m0 + k;
-      As[k][n] = (m < mend && a0 + n < N1) ? A[m * lda + a0 + n] : 0.f;
-      Bs[k][n] = (m < mend && b0 + n < N2) ? B[m * ldb + b0 + n] : 0.f;
+    for (int e = tid; e < 16 * 32; e += 256) {  // 16 rows x 32 float4
+      const int k = e >> 5, n4 = (e & 31) * 4;
+      const long long m = m0 + k;
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+      if (m < mend) {
+        if (a_vec && a0 + n4 + 3 < N1) av = *reinterpret_cast<const float4*>(A + m * lda + a0 + n4);
+        else
+          for (int c = 0; c < 4; ++c)
+            if (a0 + n4 + c < N1) (&av.x)[c] = A[m * lda + a0 + n4 + c];
+        if (b_vec && b0 + n4 + 3 < N2) bv = *reinterpret_cast<const float4*>(B + m * ldb + b0 + n4);
+        else
+          for (int c = 0; c < 4; ++c)
+            if (b0 + n4 + c < N2) (&bv.x)[c] = B[m * ldb + b0 + n4 + c];
+      }
+      *reinterpret_cast<float4*>(&As[k][n4]) = av;
+      *reinterpret_cast<float4*>(&Bs[k][n4]) = bv;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      float a[4] = {av.x, av.y, av.z, av.w};
-      float b[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float4 a0v = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1v = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b0v = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float4 b1v = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float a[8] = {a0v.x, a0v.y, a0v.z, a0v.w, a1v.x, a1v.y, a1v.z, a1v.w};
+      const float b[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int r = a0 + ty * 4 + i, c = b0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int r = a0 + ty * 8 + i;
+      const int c = b0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (r < N1 && c < N2) atomicAdd(&C[(long long)r * ldc + c], acc[i][j]);
     }
 }
 
 int launch_gemm_tn_atomic(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N1, int N2,
                           cudaStream_t s) {
-  dim3 grid(cdiv(M, TN_CHUNK), cdiv(N1, 64), cdiv(N2, 64));
-  k_gemm_tn_atomic<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N1, N2);
+  dim3 grid(cdiv(M, TN_CHUNK), cdiv(N1, 128), cdiv(N2, 128));
+  const int a_vec = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const int b_vec = (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  k_gemm_tn_atomic<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N1, N2, a_vec, b_vec);
   P2M_LAUNCH_OK();
   return P2M_OK;
 }
-
 
 // =====================================================================================
 // Thin-output Chebyshev conv (Fout <= 4, the 64 -> 3 head of the network), weights first:
@@ -456,6 +496,36 @@ int launch_thin_conv(const DevLevel& g, const float* x, int in_unpool, int rows,
   k_thin_u<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, Z, U);
   P2M_LAUNCH_OK();
   k_thin_out<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, fout, Z, U, to_dev(e), y);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// =====================================================================================
+// power-of-two scale that brings a tensor into fp16's comfortable range (tensor-core backward GEMMs)
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, long long n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));  // non-negative floats order as uints
+}
+__global__ void k_scale_from_absmax(unsigned int* io) {
+  const float m = __uint_as_float(*io);
+  float s = 1.f;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 10 - e);  // m * s in [2^9, 2^10)
+  }
+  *reinterpret_cast<float*>(io) = s;
+}
+int launch_absmax_scale(const float* x, long long n, float* scale_out, cudaStream_t s) {
+  P2M_CUDA_OK(cudaMemsetAsync(scale_out, 0, sizeof(float), s));
+  const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  k_absmax<<<grid, 256, 0, s>>>(x, n, reinterpret_cast<unsigned int*>(scale_out));
+  P2M_LAUNCH_OK();
+  k_scale_from_absmax<<<1, 1, 0, s>>>(reinterpret_cast<unsigned int*>(scale_out));
   P2M_LAUNCH_OK();
   return P2M_OK;
 }

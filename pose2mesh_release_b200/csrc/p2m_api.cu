@@ -209,6 +209,9 @@ struct BwdMap {
   float* U;
   float* dwp;
   double* sums;
+  unsigned char* wpack;   // packed fp16 K-blocks of one W_k^T (tcgen05 dT GEMM)
+  size_t wpack_bytes;
+  float* a_scale;         // power-of-two gradient scale (device scalar)
   size_t bytes;
 };
 BwdMap map_scratch(const p2m_model* m, int B, void* base) {
@@ -219,6 +222,9 @@ BwdMap map_scratch(const p2m_model* m, int B, void* base) {
   w.U = b.take<float>(s.max_U);
   w.dwp = b.take<float>(std::max(s.max_w, (size_t)1));
   w.sums = b.take<double>(2 * (size_t)s.max_f + 2 * (size_t)m->fc_out);
+  w.wpack_bytes = umma_plain_pack_bytes(256, 256);
+  w.wpack = b.take<unsigned char>(w.wpack_bytes);
+  w.a_scale = b.take<float>(4);
   w.bytes = b.off;
   return w;
 }
@@ -764,7 +770,32 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params
       const bool need_dx = !(li == 0 && dx == nullptr);
       if (need_dx) {
         Epilogue none;
-        P2M_TRY(launch_gemm(g_z, L.fout, w.wp[li], 3 * L.fin, 1, w.T, 3 * L.fin, rows, 3 * L.fin, L.fout, none, s));
+        // dT = g_z * Wp  ([rows, Fout] x [Fout, 3 Fin]).  tcgen05 path: three plain GEMMs (one per Chebyshev
+        // order, N = Fin, K = Fout) with the gradient scaled into fp16 range by a power of two.
+        if (m->precision == P2M_PREC_FP16X3_TC && umma_conv_supported(g, L.fout, L.fin) &&
+            umma_plain_pack_bytes(L.fin, L.fout) <= sc.wpack_bytes) {
+          P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
+          for (int k = 0; k < 3; ++k) {
+            // B_k[n = f][kk = o] = W[o, f*3 + k]   (reference layout, lib/models/backbones/cheby_graph_conv.py:32-37)
+            P2M_TRY(launch_umma_pack_plain(P->cl_w[li] + k, 3, 3LL * L.fin, L.fin, L.fout, sc.wpack, s));
+            UmmaConvArgs a;
+            a.g = &g;
+            a.x = g_z;
+            a.in_unpool = 0;
+            a.batch = B;
+            a.fin = L.fout;
+            a.fout = L.fin;
+            a.wpack = sc.wpack;
+            a.y = w.T;
+            a.plain = 1;
+            a.a_scale = sc.a_scale;
+            a.ldy = 3LL * L.fin;
+            a.y_col0 = k * L.fin;
+            P2M_TRY(launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s));
+          }
+        } else {
+          P2M_TRY(launch_gemm(g_z, L.fout, w.wp[li], 3 * L.fin, 1, w.T, 3 * L.fin, rows, 3 * L.fin, L.fout, none, s));
+        }
         const bool res_here = (j == 0) && blk.has_residual;
         float* out;
         int out_buf = -1;

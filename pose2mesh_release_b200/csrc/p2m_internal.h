@@ -178,6 +178,12 @@ struct UmmaConvArgs {
   const void* wpack;        // packed fp16 hi/lo weights from launch_umma_pack_weights
   Epilogue ep;
   float* y;                 // [rows, fout]
+  // plain-GEMM mode (backward dT = dz * W_k): no SpMM, x is [rows, fin] and the K-blocks come from
+  // launch_umma_pack_plain; y is written at y[r*ldy + y_col0 + n]
+  int plain = 0;
+  const float* a_scale = nullptr;   // device scalar from launch_absmax_scale (or null)
+  long long ldy = 0;                // 0: fout
+  int y_col0 = 0;
 };
 // Host: build the per-tile halo metadata of one level (uploads; device pointers appended to `owned`).
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
@@ -186,6 +192,11 @@ void set_umma_trace(long long* dev_buf);  // debug: [8][512] event log of CTA 0,
 bool umma_conv_supported(const DevLevel& g, int fin, int fout);
 size_t umma_wpack_bytes(int fin, int fout);
 int launch_umma_pack_weights(const float* W /*[fout, fin*3] ref layout*/, int fin, int fout, void* wpack, cudaStream_t s);
+// B[n][k] = Bmat[n*ld_n + k*ld_k]  (n < N, k < K, K % 32 == 0) -> fp16 [hi|lo] K-blocks, one per 32 k
+size_t umma_plain_pack_bytes(int N, int K);
+int launch_umma_pack_plain(const float* Bmat, long long ld_n, long long ld_k, int N, int K, void* wpack, cudaStream_t s);
+// scale_out[0] = 2^e with max|x| * 2^e in [2^9, 2^10)  (1 if x is all zero); scratch-free, two tiny launches
+int launch_absmax_scale(const float* x, long long n, float* scale_out, cudaStream_t s);
 int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
 
 }  // namespace p2m
