@@ -692,6 +692,313 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
   if (warp == W_MMA) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =====================================================================================
+// dW on tensor cores:  dW[o, (f,k)] = sum_rows dz[row, o] * T_k[row, f]
+//
+// The reduction runs over the ROWS, so both operands are "MN-major" for the tensor core (the K index of the
+// MMA is the mesh row).  The 128B-swizzled row-major blocks the forward kernel already builds — 128 rows x
+// [hi 32 | lo 32] fp16 of T_k for one 32-feature chunk — are exactly a canonical MN-major SWIZZLE_128B tile
+// (K = 128 rows of 128 bytes, MN = 64 elements), so the producers are shared with the forward and T is
+// recomputed on chip instead of being materialised (the SIMT path writes and re-reads 3x the activations).
+// A = dz tile, scaled by a power of two into fp16 range and split (hi, lo), stored the same way
+// ([128 rows] x 64 channels per block, two blocks per 128 channels).  Per T block: 8 K-steps x (hi, lo) MMAs
+// with M = 128 channels, N = 64 ([T_hi | T_lo] columns), accumulated in TMEM across ALL tiles of the CTA
+// (6 accumulators of 64 columns = two feature chunks per launch); one atomicAdd pass per CTA at the end.
+// =====================================================================================
+struct DwParams {
+  const float* x;
+  int in_unpool;
+  int V, P, fin;
+  int n_tiles;
+  const unsigned char* meta;
+  const int* meta_bytes;
+  int meta_stride, max_h1, max_h2;
+  const float* g;        // dz [rows, fout_total]
+  int fout_total, m_off, m_cols;
+  int chunk0, n_chunk;   // feature chunks [chunk0, chunk0 + n_chunk), n_chunk <= 2
+  const float* a_scale;  // device scalar (power of two) applied to dz before the fp16 split
+  float* dw;             // [fout_total, 3*fin], column = f*3 + k  (reference layout), accumulated atomically
+  int* status;
+};
+
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO: distance between 64-element MN groups
+  d |= (uint64_t)(1024 >> 4) << 32;                  // SBO: distance between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+constexpr int DW_NS = 3;
+constexpr int DW_G_BYTES = 4 * A_BLOCK_BYTES;  // dz tile: (hi, lo) x two 64-channel groups
+
+template <int XS>
+__global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams p) {
+  constexpr uint32_t IDESC = make_idesc_f16(TILE_M, 64) | (1u << 15) | (1u << 16);  // A and B MN-major
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;                      // [DW_NS] T blocks
+  unsigned char* gblk = ring + DW_NS * A_BLOCK_BYTES;  // dz tile blocks: hi g0, hi g1, lo g0, lo g1
+  float* Xs = reinterpret_cast<float*>(gblk + DW_G_BYTES);
+  const size_t xs_stage_floats = (size_t)p.max_h2 * FC;
+  float* T1s = Xs + XS * xs_stage_floats;
+  unsigned char* meta_s = reinterpret_cast<unsigned char*>(T1s + (size_t)p.max_h1 * FC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta_s + 2 * (size_t)p.meta_stride);
+  uint64_t* b_t_full = bars;                 // [DW_NS]
+  uint64_t* b_t_empty = b_t_full + DW_NS;    // [DW_NS]
+  uint64_t* b_x_full = b_t_empty + DW_NS;    // [XS]
+  uint64_t* b_x_empty = b_x_full + XS;       // [XS]
+  uint64_t* b_m_full = b_x_empty + XS;       // [2]
+  uint64_t* b_m_empty = b_m_full + 2;        // [2]
+  uint64_t* b_g_full = b_m_empty + 2;        // [1]
+  uint64_t* b_g_empty = b_g_full + 1;        // [1]
+  uint64_t* b_done = b_g_empty + 1;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_done + 1);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_chunk = p.n_chunk;
+  const int n_use = 3 * n_chunk;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < DW_NS; ++s) {
+      mbar_init(smem_u32(b_t_full + s), W_PROD);
+      mbar_init(smem_u32(b_t_empty + s), 1);
+    }
+    for (int s = 0; s < XS; ++s) {
+      mbar_init(smem_u32(b_x_full + s), N_XLOAD * 32);
+      mbar_init(smem_u32(b_x_empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(b_m_full + s), 1);
+      mbar_init(smem_u32(b_m_empty + s), 1);
+    }
+    mbar_init(smem_u32(b_g_full), W_PROD);
+    mbar_init(smem_u32(b_g_empty), 1);
+    mbar_init(smem_u32(b_done), 1);
+    *abort_flag = (smem_u32(ring) & 1023u) ? 1 : 0;
+    if (*abort_flag) atomicExch(p.status, 100);
+    fence_barrier_init();
+  }
+  const float a_scale = p.a_scale ? *p.a_scale : 1.f;
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= W_XLOAD && warp < W_XLOAD + N_XLOAD) {
+    // ------------------------------------------------------------ halo loaders + tile metadata (as in the forward)
+    const int lt = tid - W_XLOAD * 32;
+    const int q = lt & 7, rg = lt >> 3;
+    auto fetch_meta = [&](int it2) {
+      const int pat = (blockIdx.x + it2 * gridDim.x) % p.P;
+      const int m2 = it2 & 1;
+      mbar_wait_relaxed(smem_u32(b_m_empty + m2), ((it2 >> 1) & 1) ^ 1, abort_flag, p.status, 21);
+      const int mbytes = p.meta_bytes[pat];
+      mbar_arrive_expect_tx(smem_u32(b_m_full + m2), mbytes);
+      bulk_g2s(smem_u32(meta_s + (size_t)m2 * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
+               smem_u32(b_m_full + m2));
+    };
+    if (lt == 0 && my_tiles > 0) fetch_meta(0);
+    uint32_t g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / p.P;
+      const int m = it & 1;
+      mbar_wait_relaxed(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 22);
+      const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
+      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
+      const int h2 = hdr->h2;
+      const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);
+      const long long mesh_row0 = (long long)b * p.V;
+      for (int c = 0; c < n_chunk; ++c, ++g) {
+        const int xs = g % XS;
+        mbar_wait_relaxed(smem_u32(b_x_empty + xs), ((g / XS) & 1) ^ 1, abort_flag, p.status, 23);
+        const uint32_t dst0 = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
+        const float* src0 = p.x + (p.chunk0 + c) * FC + q * 4;
+        for (int i = rg; i < h2; i += 8) {
+          const int v = halo[i];
+          if (v >= 0) {
+            long long r = mesh_row0 + v;
+            if (p.in_unpool) r >>= 1;
+            cp_async16(dst0 + i * 128, src0 + r * p.fin);
+          } else {
+            sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+        cp_async_arrive_noinc(smem_u32(b_x_full + xs));
+        if (c == 0 && lt == 0 && it + 1 < my_tiles) fetch_meta(it + 1);
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t ucnt = 0;
+      const uint32_t g_hi = smem_u32(gblk), g_lo = g_hi + 2 * A_BLOCK_BYTES;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(smem_u32(b_g_full), it & 1, abort_flag, p.status, 24);
+        tc_fence_after();
+        for (int u = 0; u < n_use; ++u, ++ucnt) {
+          const int s = ucnt % DW_NS;
+          mbar_wait(smem_u32(b_t_full + s), (ucnt / DW_NS) & 1, abort_flag, p.status, 25);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(u * 64);
+          const uint64_t dt = make_desc_sw128_mn(smem_u32(ring + s * A_BLOCK_BYTES), A_BLOCK_BYTES);
+          const uint64_t dh = make_desc_sw128_mn(g_hi, A_BLOCK_BYTES), dl = make_desc_sw128_mn(g_lo, A_BLOCK_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // 16 mesh rows per K step = 2048 bytes = +128 in the address field
+            umma_f16(d_tmem, dh + ks * 128, dt + ks * 128, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(d_tmem, dl + ks * 128, dt + ks * 128, IDESC, 1u);
+          }
+          umma_commit(smem_u32(b_t_empty + s));
+        }
+        umma_commit(smem_u32(b_g_empty));  // the dz blocks may be overwritten once these MMAs have read them
+      }
+      umma_commit(smem_u32(b_done));
+    }
+  } else if (warp >= W_EPI0) {
+    // ------------------------------------------------------------ final reduction: TMEM -> atomicAdd into dW
+    const int lane_base = (warp & 3) * 32;
+    const int o_local = lane_base + lane;
+    mbar_wait_relaxed(smem_u32(b_done), 0, abort_flag, p.status, 26);
+    tc_fence_after();
+    const float inv = 1.f / a_scale;
+    const bool valid = (o_local < p.m_cols) && (my_tiles > 0);
+    float* drow = p.dw + (size_t)(p.m_off + o_local) * 3 * p.fin;
+    for (int u = 0; u < n_use; ++u) {
+      const int c = u / 3, k = u - 3 * c;
+      uint32_t hi[32], lo[32];
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 64), hi);
+      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 64 + 32), lo);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int f = (p.chunk0 + c) * FC + j;
+          atomicAdd(drow + f * 3 + k, (__uint_as_float(hi[j]) + __uint_as_float(lo[j])) * inv);
+        }
+      }
+    }
+  } else if (warp < W_PROD) {
+    // ------------------------------------------------------------ producers
+    const int q = tid & 7, rg = tid >> 3;
+    const uint32_t t1s_a = smem_u32(T1s), ring_a = smem_u32(ring), g_a = smem_u32(gblk);
+    uint32_t ucnt = 0, gcnt = 0;
+    constexpr int T1_ROWS = 4;
+    uint32_t t1_row[T1_ROWS], t1_e[T1_ROWS];
+    uint32_t row0 = 0, row1 = 0, r0e = 0, r1e = 0, ent_a = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int b = tile / p.P, pat = tile - b * p.P;
+      const int m = it & 1;
+      mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 27);
+      {
+        const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
+        const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
+        const uint32_t mb_a = smem_u32(mb);
+        const uint32_t rp_a = mb_a + hdr->off_rp, ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
+        ent_a = mb_a + hdr->off_ent;
+        const int h1 = hdr->h1;
+#pragma unroll
+        for (int t = 0; t < T1_ROWS; ++t) {
+          const int j = rg + 64 * t;
+          t1_row[t] = 0xFFFFu;
+          if (j < h1) {
+            const uint32_t i = lds_u16(ord1_a + 2 * j);
+            t1_row[t] = i;
+            t1_e[t] = lds_u16(rp_a + 2 * i) | (lds_u16(rp_a + 2 * i + 2) << 16);
+          }
+        }
+        row0 = lds_u16(ord2_a + 2 * rg);
+        row1 = lds_u16(ord2_a + 2 * (64 + rg));
+        r0e = lds_u16(rp_a + 2 * row0) | (lds_u16(rp_a + 2 * row0 + 2) << 16);
+        r1e = lds_u16(rp_a + 2 * row1) | (lds_u16(rp_a + 2 * row1 + 2) << 16);
+      }
+      // dz tile -> (hi, lo) fp16 blocks, MN-major [row][channel]
+      mbar_wait(smem_u32(b_g_empty), (it & 1) ^ 1, abort_flag, p.status, 28);
+      {
+        const int n_rows = min(TILE_M, p.V - pat * TILE_M);
+        const long long r_base = (long long)b * p.V + (long long)pat * TILE_M;
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int i = ps * 64 + rg;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int col = q * 4 + 32 * jj;  // channel inside this launch's 128-channel slice
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_rows && col < p.m_cols)
+              v = *reinterpret_cast<const float4*>(p.g + (r_base + i) * p.fout_total + p.m_off + col);
+            v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            const uint32_t off = (uint32_t)(col >> 6) * A_BLOCK_BYTES + sw128_off(i, (col & 63) >> 3) + ((col >> 2) & 1) * 8;
+            sts_u2(g_a + off, hi);
+            sts_u2(g_a + 2 * A_BLOCK_BYTES + off, lo);
+          }
+        }
+        fence_async_proxy();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_u32(b_g_full));
+      }
+      for (int c = 0; c < n_chunk; ++c, ++gcnt) {
+        const int xs = gcnt % XS;
+        mbar_wait(smem_u32(b_x_full + xs), (gcnt / XS) & 1, abort_flag, p.status, 29);
+        const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
+        const uint32_t t1s_q = t1s_a + q * 16;
+#pragma unroll
+        for (int t = 0; t < T1_ROWS; ++t) {
+          if (t1_row[t] != 0xFFFFu)
+            sts_f4(t1s_q + t1_row[t] * 128, gather_row4(ent_a, t1_e[t] & 0xFFFFu, t1_e[t] >> 16, xs_q));
+        }
+        producer_barrier();
+        float4 tv[3][2];
+        {
+          const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
+          const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
+          tv[0][0] = lds_f4(xs_q + row0 * 128);
+          tv[0][1] = lds_f4(xs_q + row1 * 128);
+          tv[1][0] = lds_f4(t1s_q + row0 * 128);
+          tv[1][1] = lds_f4(t1s_q + row1 * 128);
+          const float4 a = tv[0][0], c2 = tv[0][1];
+          tv[2][0] = make_float4(2.f * g0.x - a.x, 2.f * g0.y - a.y, 2.f * g0.z - a.z, 2.f * g0.w - a.w);
+          tv[2][1] = make_float4(2.f * g1.x - c2.x, 2.f * g1.y - c2.y, 2.f * g1.z - c2.z, 2.f * g1.w - c2.w);
+        }
+        const uint32_t u0 = ucnt;
+#pragma unroll
+        for (int k = 0; k < 3; ++k, ++ucnt) {
+          const int s = ucnt % DW_NS;
+          mbar_wait(smem_u32(b_t_empty + s), ((ucnt / DW_NS) & 1) ^ 1, abort_flag, p.status, 30);
+          const uint32_t blk = ring_a + s * A_BLOCK_BYTES + (q & 1) * 8;
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            const uint32_t i = ps ? row1 : row0;
+            uint2 hi, lo;
+            split4(tv[k][ps], hi, lo);
+            sts_u2(blk + sw128_off(i, q >> 1), hi);
+            sts_u2(blk + sw128_off(i, 4 + (q >> 1)), lo);
+          }
+        }
+        fence_async_proxy();
+        __syncwarp();
+        if ((tid & 31) == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) mbar_arrive(smem_u32(b_t_full + (u0 + k) % DW_NS));
+        }
+        producer_barrier();
+        if (tid == 0) {
+          mbar_arrive(smem_u32(b_x_empty + xs));
+          if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+}
+
 // fp32 reference-layout weights [Fout, Fin*3] (column = f*3+k) -> K-blocks of fp16 [Whi | Wlo]
 // in the exact shared-memory image (128B-swizzled), block u = chunk*3 + k, so the kernel can
 // fetch a block with a single cp.async.bulk.
@@ -886,6 +1193,60 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
 }
 
 void set_umma_trace(long long* dev_buf) { g_umma_trace = dev_buf; }
+
+size_t dw_smem_bytes(int XS, const DevLevel& g) {
+  return 1024 + (size_t)DW_NS * A_BLOCK_BYTES + DW_G_BYTES + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +
+         2 * (size_t)g.meta_stride + 8 * (2 * DW_NS + 2 * XS + 8) + 32;
+}
+
+bool umma_dw_supported(const DevLevel& g, int fin, int fout) {
+  if (g.tile_meta == nullptr || g.n_pattern <= 0 || g.max_h1 > 256) return false;
+  if (fin % FC != 0 || fin < FC || fin > 256) return false;
+  if (fout != 64 && fout != 128 && fout != 256) return false;
+  return dw_smem_bytes(1, g) <= SMEM_LIMIT;
+}
+
+int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout, const float* dz,
+                   const float* a_scale, float* dw_ref, int* status, int sm_count, cudaStream_t s) {
+  if (!umma_dw_supported(g, fin, fout)) {
+    set_error("umma_dw: unsupported shape");
+    return P2M_ERR_INVALID;
+  }
+  const int xs = dw_smem_bytes(2, g) <= SMEM_LIMIT ? 2 : 1;
+  const size_t smem = dw_smem_bytes(xs, g);
+  auto kern = (xs == 2) ? k_cheb_dw_umma<2> : k_cheb_dw_umma<1>;
+  P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DwParams p;
+  p.x = x;
+  p.in_unpool = in_unpool;
+  p.V = g.V;
+  p.P = g.n_pattern;
+  p.fin = fin;
+  p.n_tiles = batch * g.n_pattern;
+  p.meta = g.tile_meta;
+  p.meta_bytes = g.tile_meta_bytes;
+  p.meta_stride = g.meta_stride;
+  p.max_h1 = g.max_h1;
+  p.max_h2 = g.max_h2;
+  p.g = dz;
+  p.fout_total = fout;
+  p.a_scale = a_scale;
+  p.dw = dw_ref;
+  p.status = status;
+  const int grid = std::min(p.n_tiles, sm_count);
+  const int total_chunks = fin / FC;
+  for (int m_off = 0; m_off < fout; m_off += 128) {
+    p.m_off = m_off;
+    p.m_cols = std::min(128, fout - m_off);
+    for (int c0 = 0; c0 < total_chunks; c0 += 2) {
+      p.chunk0 = c0;
+      p.n_chunk = std::min(2, total_chunks - c0);
+      kern<<<grid, NUM_THREADS2, smem, s>>>(p);
+      P2M_LAUNCH_OK();
+    }
+  }
+  return P2M_OK;
+}
 
 bool umma_conv_supported(const DevLevel& g, int fin, int fout) {
   if (g.tile_meta == nullptr || g.n_pattern <= 0) return false;

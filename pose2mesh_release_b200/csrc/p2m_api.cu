@@ -761,20 +761,30 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params
         gz_buf = tgt;
       }
       P2M_TRY(launch_col_sum(g_z, rows, L.fout, sc.sums, G->cl_b[li], s));
-      // dW: recompute the basis of the layer input, dWp = g_z^T T
-      P2M_TRY(launch_cheb_basis(g, inp, in_unpool, rows, L.fin, w.T, s));
-      P2M_TRY(launch_fill_zero(sc.dwp, sizeof(float) * L.fout * 3 * L.fin, s));
-      P2M_TRY(launch_gemm_tn_atomic(g_z, L.fout, w.T, 3 * L.fin, sc.dwp, 3 * L.fin, rows, L.fout, 3 * L.fin, s));
-      P2M_TRY(launch_unpermute_w(sc.dwp, G->cl_w[li], L.fout, L.fin, s));
+      // dW.  tcgen05 path: the basis is rebuilt on chip by the forward's producers and contracted with the
+      // (power-of-two scaled) dz tile by MN-major UMMAs; otherwise SIMT: materialise T, dWp = g_z^T T.
+      const bool tc = (m->precision == P2M_PREC_FP16X3_TC);
+      bool have_scale = false;
+      if (tc && umma_dw_supported(g, L.fin, L.fout)) {
+        P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
+        have_scale = true;
+        P2M_TRY(launch_fill_zero(G->cl_w[li], sizeof(float) * L.fout * 3 * L.fin, s));
+        P2M_TRY(launch_umma_dw(g, inp, in_unpool, B, L.fin, L.fout, g_z, sc.a_scale, G->cl_w[li], m->kernel_status,
+                               m->sm_count, s));
+      } else {
+        P2M_TRY(launch_cheb_basis(g, inp, in_unpool, rows, L.fin, w.T, s));
+        P2M_TRY(launch_fill_zero(sc.dwp, sizeof(float) * L.fout * 3 * L.fin, s));
+        P2M_TRY(launch_gemm_tn_atomic(g_z, L.fout, w.T, 3 * L.fin, sc.dwp, 3 * L.fin, rows, L.fout, 3 * L.fin, s));
+        P2M_TRY(launch_unpermute_w(sc.dwp, G->cl_w[li], L.fout, L.fin, s));
+      }
       // dX
       const bool need_dx = !(li == 0 && dx == nullptr);
       if (need_dx) {
         Epilogue none;
         // dT = g_z * Wp  ([rows, Fout] x [Fout, 3 Fin]).  tcgen05 path: three plain GEMMs (one per Chebyshev
         // order, N = Fin, K = Fout) with the gradient scaled into fp16 range by a power of two.
-        if (m->precision == P2M_PREC_FP16X3_TC && umma_conv_supported(g, L.fout, L.fin) &&
-            umma_plain_pack_bytes(L.fin, L.fout) <= sc.wpack_bytes) {
-          P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
+        if (tc && umma_conv_supported(g, L.fout, L.fin) && umma_plain_pack_bytes(L.fin, L.fout) <= sc.wpack_bytes) {
+          if (!have_scale) P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
           for (int k = 0; k < 3; ++k) {
             // B_k[n = f][kk = o] = W[o, f*3 + k]   (reference layout, lib/models/backbones/cheby_graph_conv.py:32-37)
             P2M_TRY(launch_umma_pack_plain(P->cl_w[li] + k, 3, 3LL * L.fin, L.fin, L.fout, sc.wpack, s));

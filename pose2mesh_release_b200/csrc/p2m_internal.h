@@ -197,6 +197,10 @@ size_t umma_plain_pack_bytes(int N, int K);
 int launch_umma_pack_plain(const float* Bmat, long long ld_n, long long ld_k, int N, int K, void* wpack, cudaStream_t s);
 // scale_out[0] = 2^e with max|x| * 2^e in [2^9, 2^10)  (1 if x is all zero); scratch-free, two tiny launches
 int launch_absmax_scale(const float* x, long long n, float* scale_out, cudaStream_t s);
+// dW[o, f*3+k] += sum_rows dz[row,o] * T_k(x)[row,f] on tensor cores (dw_ref zeroed by the caller)
+bool umma_dw_supported(const DevLevel& g, int fin, int fout);
+int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout, const float* dz,
+                   const float* a_scale, float* dw_ref, int* status, int sm_count, cudaStream_t s);
 int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
 
 }  // namespace p2m
