@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=24, help="meshes in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
+    ap.add_argument("--mesh", default="smpl", choices=["smpl", "mano"],
+                    help="smpl: 6890-vertex SMPL-size hierarchy (default, BASELINE configs[1,2,4]); "
+                         "mano: 778-vertex MANO-size hierarchy 1088..68, 21 joints (configs[3], use --batch 1024)")
     return ap.parse_args()
 
 
@@ -112,9 +115,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem():
+def build_problem(mesh="smpl"):
     from pose2mesh_release_b200 import graph as pg
 
+    if mesh == "mano":
+        face = pg.synthetic_sphere_faces(778, 1)
+        _, graph_L, _, perm_rev = pg.build_coarse_graphs(face, 21, pg.MANO_SKELETON, pg.MANO_HORI_CONN, levels=6)
+        return graph_L, perm_rev
     face = pg.synthetic_sphere_faces(MESH["n_vertex"], MESH["seed"])
     _, graph_L, _, perm_rev = pg.build_coarse_graphs(face, 17, pg.H36M_SKELETON, pg.H36M_FLIP_PAIRS,
                                                      levels=MESH["levels"])
@@ -252,14 +259,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    graph_L, perm_rev = build_problem()
+    graph_L, perm_rev = build_problem(args.mesh)
+    n_joint = 21 if args.mesh == "mano" else 17
     torch.manual_seed(123)
-    model = Pose2Mesh(5, 3, graph_L, joint_set="human36")
+    model = Pose2Mesh(5, 3, graph_L, joint_set="mano" if args.mesh == "mano" else "human36")
     model.load_state_dict(randomize_bn_({k: v.clone() for k, v in model.state_dict().items()}))
     model = model.to(dev).set_precision(args.precision)
     B = args.batch
     g = torch.Generator().manual_seed(1000 + rank)
-    x_host = torch.randn(B, 17, 5, generator=g).pin_memory()
+    x_host = torch.randn(B, n_joint, 5, generator=g).pin_memory()
     x = x_host.to(dev)
     hbm_gbs, bf16_tf, peak_src = measured_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -402,11 +410,12 @@ def main():
             layers.append({"layer": li, "V": d["V"], "fin": d["fin"], "fout": d["fout"], "ms": round(float(ms), 4),
                            "GBps": round(byt / ms * 1e-6, 1), "TFLOPs": round(fl / ms * 1e-9, 1)})
         dom = [i for i, d in enumerate(info) if d["V"] == info[-1]["V"] and d["fin"] == 128 and d["fout"] == 128]
+        nnz0 = int(graph_L[0].nnz)
         if dom:
             ms = float(np.mean([acc[i] for i in dom]))
             d = info[dom[0]]
             byt = 4.0 * d["V"] * (d["fin"] + d["fout"]) * B          # 4*V*(Fin+Fout) per mesh
-            fl = (2.0 * d["V"] * 3 * d["fin"] * d["fout"] + 2.0 * (2 * 53616 * d["fin"]) + 2.0 * d["V"] * d["fin"]) * B
+            fl = (2.0 * d["V"] * 3 * d["fin"] * d["fout"] + 2.0 * (2 * nnz0 * d["fin"]) + 2.0 * d["V"] * d["fin"]) * B
             ach = byt / (ms * 1e-3) * 1e-9
             roofline = {"bound": "hbm", "kernel": f"cheb conv V={d['V']} {d['fin']}->{d['fout']} K=3 (layers {dom})",
                         "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": None,
@@ -416,7 +425,7 @@ def main():
                         "note": "layer time includes the weight pack/permute launches (<1%); precision " + args.precision}
 
     cpu_baseline = None
-    if rank == 0 and args.cpu_sample > 0 and args.mode == "fwd":
+    if rank == 0 and args.cpu_sample > 0 and args.mode == "fwd" and args.mesh == "smpl":
         v, dt, used = cpu_port_meshes_per_s(graph_L, args.cpu_sample)
         cpu_baseline = {"value": v, "unit": "meshes/s", "cores": used, "kind": "port", "host_cores": os.cpu_count(),
                         "sample": f"{args.cpu_sample} meshes, eval forward, CPU oracle (torch CPU kernels), {dt:.1f} s; "
@@ -429,9 +438,13 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tcgen05 fp16x3 split, fp32 accumulate)" if args.precision == "fp16x3" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.mode == "fwd" else
+            "config": {"workload": ("configs[3]: MANO-size hierarchy 1088..68 (778 verts), 21 joints, "
+                                    + ("forward (eval)" if args.mode == "fwd" else "forward+backward, L1 loss"))
+                       if args.mesh == "mano" else WORKLOAD if args.mode == "fwd" else
                        "configs[2]/[4]: B=256/GPU fwd+bwd, L1 loss, train-mode BatchNorm, one NCCL all-reduce of the flat gradient",
-                       "batch_per_gpu": B, "global_batch": B * world, "mesh": "synthetic genus-0, 6890 verts, seed 2",
+                       "batch_per_gpu": B, "global_batch": B * world,
+                       "mesh": "synthetic genus-0, 778 verts, seed 1 (MANO-size)" if args.mesh == "mano"
+                       else "synthetic genus-0, 6890 verts, seed 2",
                        "levels": [int(m.shape[0]) for m in graph_L], "precision": args.precision,
                        "parallelism": f"dp{world} (independent shards, no data-path collective)" if args.mode == "fwd"
                        else f"dp{world} (single all-reduce per step)",
