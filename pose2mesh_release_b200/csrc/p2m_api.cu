@@ -928,15 +928,48 @@ int p2m_cheb_conv_bwd(p2m_model_t* m, const p2m_conv_bwd_args_t* a, void* worksp
   float* U = b.take<float>(rows * fin);
   b.take<float>(rows * fout);
   double* sums = b.take<double>(2 * (size_t)std::max(fin, fout));
+  float* sc2 = b.take<float>(2 * (size_t)fout);
+  unsigned char* wpack = b.take<unsigned char>(umma_wpack_bytes(((fin + 31) / 32) * 32, fout) + 16);
+  float* a_scale = sc2;  // device scalar for the tensor-core paths (the forward's scale/shift slot is free here)
+  const bool tc = (m->precision == P2M_PREC_FP16X3_TC);
+  bool have_scale = false;
   P2M_TRY(launch_col_sum(a->dz, (int)rows, fout, sums, a->dbias, s));
-  P2M_TRY(launch_cheb_basis(g, a->x, 0, (int)rows, fin, T, s));
-  P2M_TRY(launch_fill_zero(dwp, sizeof(float) * fout * 3 * fin, s));
-  P2M_TRY(launch_gemm_tn_atomic(a->dz, fout, T, 3 * fin, dwp, 3 * fin, (int)rows, fout, 3 * fin, s));
-  P2M_TRY(launch_unpermute_w(dwp, a->dweight, fout, fin, s));
+  if (tc && umma_dw_supported(g, fin, fout)) {
+    P2M_TRY(launch_absmax_scale(a->dz, (long long)rows * fout, a_scale, s));
+    have_scale = true;
+    P2M_TRY(launch_fill_zero(a->dweight, sizeof(float) * fout * 3 * fin, s));
+    P2M_TRY(launch_umma_dw(g, a->x, 0, a->batch, fin, fout, a->dz, a_scale, a->dweight, m->kernel_status, m->sm_count, s));
+  } else {
+    P2M_TRY(launch_cheb_basis(g, a->x, 0, (int)rows, fin, T, s));
+    P2M_TRY(launch_fill_zero(dwp, sizeof(float) * fout * 3 * fin, s));
+    P2M_TRY(launch_gemm_tn_atomic(a->dz, fout, T, 3 * fin, dwp, 3 * fin, (int)rows, fout, 3 * fin, s));
+    P2M_TRY(launch_unpermute_w(dwp, a->dweight, fout, fin, s));
+  }
   if (a->dx) {
     Epilogue none;
-    P2M_TRY(launch_permute_w(a->weight, wp, fout, fin, s));
-    P2M_TRY(launch_gemm(a->dz, fout, wp, 3 * fin, 1, T, 3 * fin, (int)rows, 3 * fin, fout, none, s));
+    if (tc && umma_conv_supported(g, fout, fin) && umma_plain_pack_bytes(fin, fout) <= umma_wpack_bytes(((fin + 31) / 32) * 32, fout)) {
+      if (!have_scale) P2M_TRY(launch_absmax_scale(a->dz, (long long)rows * fout, a_scale, s));
+      for (int k = 0; k < 3; ++k) {
+        P2M_TRY(launch_umma_pack_plain(a->weight + k, 3, 3LL * fin, fin, fout, wpack, s));
+        UmmaConvArgs u;
+        u.g = &g;
+        u.x = a->dz;
+        u.in_unpool = 0;
+        u.batch = a->batch;
+        u.fin = fout;
+        u.fout = fin;
+        u.wpack = wpack;
+        u.y = T;
+        u.plain = 1;
+        u.a_scale = a_scale;
+        u.ldy = 3LL * fin;
+        u.y_col0 = k * fin;
+        P2M_TRY(launch_umma_conv(u, m->kernel_status, m->zero_row, m->sm_count, s));
+      }
+    } else {
+      P2M_TRY(launch_permute_w(a->weight, wp, fout, fin, s));
+      P2M_TRY(launch_gemm(a->dz, fout, wp, 3 * fin, 1, T, 3 * fin, (int)rows, 3 * fin, fout, none, s));
+    }
     P2M_TRY(launch_cheb_basis_bwd(g, T, (int)rows, fin, U, nullptr, 0, nullptr, 0, a->dx, s));
   }
   return P2M_OK;

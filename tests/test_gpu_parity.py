@@ -332,3 +332,47 @@ def test_fused_output_gather_matches_indexing():
         picked = model.forward_vertices(x, perm_rev, n_real)
     assert picked.shape == (3, n_real, 3)
     assert torch.equal(picked, full[:, torch.as_tensor(perm_rev[:n_real], device=dev()), :])
+
+
+BWD_SHAPES = [
+    ("smpl_small", 0, 2, 128, 128),   # V=2048, two feature-chunk passes
+    ("smpl_small", 1, 2, 256, 256),   # V=1024: four passes x two 128-channel halves
+    ("smpl_small", 2, 3, 256, 128),
+    ("smpl_small", 3, 2, 64, 128),
+    ("mano_like", 0, 2, 128, 64),     # ragged tiles, Fout = 64 (zero-padded dz block)
+    ("mano_like", 1, 2, 32, 256),
+]
+
+
+@pytest.mark.parametrize("case", BWD_SHAPES, ids=lambda c: f"{c[0]}-L{c[1]}-B{c[2]}-{c[3]}to{c[4]}")
+def test_tcgen05_conv_backward_matches_oracle(case):
+    """dT (plain-GEMM mode) and dW (MN-major UMMA, TMEM accumulation over tiles) on one layer, with gradients of
+    realistic size (1e-6: exercises the power-of-two scaling into fp16 range), against autograd over the oracle."""
+    from oracle import meshnet_oracle as mo
+    from pose2mesh_release_b200 import cheby_graph_conv as cgc
+
+    name, level, b, fin, fout = case
+    mats, _ = graph_from_fixture(name)
+    L = mats[level]
+    lap = mo.laplacians_to_torch([L], drop_second_coarsest=False)[0]
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(b, L.shape[0], fin, generator=g)
+    w = (torch.rand(fout, 3 * fin, generator=g) * 2 - 1) * float(np.sqrt(2.0 / (3 * fin + fout)))
+    bias = torch.zeros(fout)
+    gy = torch.randn(b, L.shape[0], fout, generator=g) * 1e-6
+    cl = torch.nn.Linear(3 * fin, fout).to(dev())
+    cl.weight.data.copy_(w)
+    cl.bias.data.copy_(bias)
+    cgc.set_default_precision("fp16x3")
+    try:
+        gh = cgc.graph_handle(L)
+        xg = x.to(dev()).requires_grad_(True)
+        y = cgc.graph_conv_cheby(xg, cl, None, L, fout, 3)
+        y.backward(gy.to(dev()))
+        assert gh.kernel_status(0) == 0
+    finally:
+        cgc.set_default_precision("fp32")
+    xo, wo = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    mo.cheb_conv(xo, lap, wo, bias).backward(gy)
+    assert rel_err(xg.grad, xo.grad) < 1e-5
+    assert rel_err(cl.weight.grad, wo.grad) < 1e-5
