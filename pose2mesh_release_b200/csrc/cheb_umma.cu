@@ -1,25 +1,30 @@
-// tcgen05 (5th-gen tensor core) Chebyshev graph convolution for sm_100a — ONE kernel per layer:
+// tcgen05 (5th-gen tensor core) kernels of the MeshNet hot path for sm_100a.
+//
+// k_cheb_conv_umma — ONE kernel per Chebyshev graph-conv layer:
 //
 //   Y[tile] = epilogue( [T0 | T1 | T2](X)[tile] * W^T ),   T1 = L~ X, T2 = 2 L~ T1 - X
 //
-// A CTA owns a tile of 128 consecutive vertices of one mesh (a compact patch: the reference's
-// binary-tree vertex order makes rows [128p,128p+128) the descendants of one coarse node).
-//   * 8 producer warps build the A operand on chip, 32 features at a time: they stage the tile's
-//     2-hop halo of X in shared memory (cp.async, 128 B per row = one cache line), run the two
-//     sparse products out of shared memory with a tile-local CSR, split every fp32 value into an
-//     fp16 (hi, lo) pair and write it straight into the 128B-swizzled K-major UMMA layout.
+// One persistent CTA per SM; a tile is 128 consecutive vertices of one mesh (a compact patch: the
+// reference's binary-tree vertex order makes rows [128p,128p+128) the descendants of one coarse node).
+//   * 16 producer warps build the A operand on chip, 32 features at a time: out of the staged 2-hop halo of
+//     X they run the two sparse products from shared memory with a tile-local CSR, split every fp32 value
+//     into an fp16 (hi, lo) pair and write it straight into the 128B-swizzled K-major UMMA layout.
 //     T0/T1/T2 are never materialised in HBM.
+//   * 2 loader warps stage the halo rows with 16-byte cp.async copies one chunk ahead (completion through
+//     cp.async.mbarrier.arrive.noinc) and prefetch the next tile's metadata blob with cp.async.bulk.
 //   * 1 thread streams the pre-packed fp16 (hi|lo) weight blocks with cp.async.bulk (TMA engine,
 //     mbarrier complete_tx).
-//   * 1 thread issues tcgen05.mma (kind::f16, M=128, N=Fout, K=16) into a TMEM accumulator:
-//     per 16 features three MMAs — hi*Whi + lo*Whi + hi*Wlo — i.e. an error-compensated product
-//     with ~2^-21 relative error, which is what keeps the 1e-4 fp32 parity bar (plain TF32/FP16
-//     does not, SURVEY.md §7 "hard parts" 1).
-//   * the 8 producer warps then drain TMEM (tcgen05.ld) through the fused epilogue: bias /
-//     folded BatchNorm, ReLU, channel-resampled residual, and store.
-// The unpool between levels is virtual: with in_unpool the halo rows are read from row r>>1 of the
-// coarser tensor.  Accumulation is fp32 in TMEM; weights are pre-scaled by 2^6 so that their lo
-// parts stay normal fp16 numbers (undone exactly in the epilogue).
+//   * 1 thread issues tcgen05.mma (kind::f16, M=128, N=Fout, K=16) into a double-buffered TMEM accumulator:
+//     per 16 features three MMAs — hi*Whi + lo*Whi + hi*Wlo — an error-compensated product with ~2^-21
+//     relative error, which is what keeps the 1e-4 fp32 parity bar (plain TF32/FP16 does not, SURVEY.md §7
+//     "hard parts" 1).
+//   * 4 epilogue warps drain TMEM (tcgen05.ld) through the fused epilogue — bias / folded BatchNorm, ReLU,
+//     channel-resampled residual — while the next tile's main loop runs.
+// The unpool between levels is virtual: with in_unpool the halo rows are read from row r>>1 of the coarser
+// tensor.  Weights are pre-scaled by 2^6 so that their lo parts stay normal fp16 numbers (undone exactly in the
+// epilogue).  The same kernel in `plain` mode is the backward dT GEMM; k_cheb_dw_umma (below) is the dW
+// reduction with MN-major operands.  Every mbarrier wait is time-bounded (a protocol bug sets a status word
+// instead of hanging the GPU) and tools/umma_trace.py dumps a per-role event timeline of CTA 0.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -198,21 +203,6 @@ __device__ __forceinline__ float4 gather_row4(uint32_t ent, uint32_t e, uint32_t
     fma4(acc0, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
   }
   return make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
-}
-// acc += sum_e val[e] * rows[slot[e]][q]  over the CSR entries [e, e1) of one row; `rows` = staged X or T1
-__device__ __forceinline__ float4 gather_row(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (; e + 1 < e1; e += 2) {
-    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8);
-    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x);
-    fma4(acc, __uint_as_float(a0.y), x0);
-    fma4(acc, __uint_as_float(a1.y), x1);
-  }
-  if (e < e1) {
-    const uint2 a0 = lds_u2(ent + e * 8);
-    fma4(acc, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
-  }
-  return acc;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
