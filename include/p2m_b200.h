@@ -89,6 +89,8 @@ int p2m_model_layer_times_ms(p2m_model_t* m, float* out_ms, int n);
 int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out);
 /* Debug: CTA 0 of the tcgen05 kernels logs (event << 48 | SM clock) into dev_buf [8][512] int64; NULL = off. */
 int p2m_debug_set_trace(void* dev_buf);
+/* Debug / ablation: 1 (default) = T1 = L~x as a separate pass + conv with given T1; 0 = fully fused conv.   */
+int p2m_debug_set_split_t1(p2m_model_t* m, int enable);
 
 /* Bytes of device workspace p2m_meshnet_forward needs for batch B.  In training mode the workspace
  * also carries what p2m_meshnet_backward reads, so it must stay alive and untouched in between.   */

@@ -25,10 +25,12 @@
 // epilogue).  The same kernel in `plain` mode is the backward dT GEMM; k_cheb_dw_umma (below) is the dW
 // reduction with MN-major operands.  Every mbarrier wait is time-bounded (a protocol bug sets a status word
 // instead of hanging the GPU) and tools/umma_trace.py dumps a per-role event timeline of CTA 0.
+#include <cuda.h>  // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -139,6 +141,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// One 2-D tiled TMA load (box = 32 floats x box rows of the tensor map) into dense 128-byte rows.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   // the mbarrier gets this thread's arrival once all of its earlier cp.async copies have landed
@@ -288,6 +300,9 @@ struct KParams {
   const float* zero_row;  // 128 bytes of zeros: source of the empty halo slots of ragged tiles
   EpiDev ep;
   int res_identity;       // residual resampling is the identity (Fin_block == Fout): vector path
+  const float* t1;        // optional precomputed T1 = L~ x, [rows, fin] at LOGICAL rows (k_cheb_t1): the conv kernel
+                          // then stages the tile's own X rows and the T1 rows of its 1-hop halo, and only runs the
+                          // second sparse product on chip (no halo recomputation of T1)
   int plain;              // 1: plain GEMM y = x * B^T (no SpMM): one K-block per chunk, rows = the tile's own
   const float* a_scale;   // optional device scalar: x is multiplied by it before the fp16 split (power of two,
                           // chosen from max|x|: gradients are far below fp16's range) and divided out afterwards
@@ -296,6 +311,9 @@ struct KParams {
   float* y;
   int* status;
   long long* trace;  // optional [8][512] event log of CTA 0 (debug): (event << 48) | clock
+  int tma;           // 1: the tile's own rows of x (and t1) arrive by one 2-D TMA load each (T1-given / plain mode on
+                     //    levels whose size is a multiple of 128); with in_unpool the x box is the 64 source rows
+  CUtensorMap tm_x, tm_t1;
 };
 
 __device__ __forceinline__ void trace_ev(const KParams& p, int role, int& n, int ev) {
@@ -317,7 +335,7 @@ constexpr int W_XLOAD = 16, N_XLOAD = 2, W_BLOAD = 18, W_MMA = 19, W_EPI0 = 20;
 constexpr int NUM_THREADS2 = 24 * 32;
 
 template <int N, int NS, int XS>
-__global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParams p) {
+__global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid_constant__ KParams p) {
   constexpr int B_BLOCK_BYTES = N * 128;
   constexpr int SLOT_BYTES = A_BLOCK_BYTES + B_BLOCK_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16(TILE_M, N);
@@ -325,10 +343,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;  // 128B-swizzled blocks need 1024-byte alignment (checked below)
-  float* Xs = reinterpret_cast<float*>(ring + NS * SLOT_BYTES);                 // [XS][max_h2][32]
-  const size_t xs_stage_floats = (size_t)p.max_h2 * FC;
-  float* T1s = Xs + XS * xs_stage_floats;                                       // [max_h1][32]
-  unsigned char* meta_s = reinterpret_cast<unsigned char*>(T1s + (size_t)p.max_h1 * FC);  // [2][meta_stride]
+  const bool t1g = (p.t1 != nullptr);
+  float* Xs = reinterpret_cast<float*>(ring + NS * SLOT_BYTES);                 // [XS][max_h2 | 128][32]
+  const size_t xs_stage_floats = (size_t)((t1g || p.plain) ? TILE_M : p.max_h2) * FC;
+  float* T1s = Xs + XS * xs_stage_floats;                                       // [1 | XS | 0][max_h1][32]
+  const size_t t1_stage_floats = (size_t)p.max_h1 * FC;
+  unsigned char* meta_s =
+      reinterpret_cast<unsigned char*>(T1s + (p.plain ? 0 : (t1g ? XS : 1)) * t1_stage_floats);  // [2][meta_stride]
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta_s + 2 * (size_t)p.meta_stride);
   // barrier map
   uint64_t* b_ab_full = bars;                // [NS]
@@ -343,6 +364,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
   float* ep_mul = reinterpret_cast<float*>(tmem_slot + 4);  // [N] acc * mul + add  (weight scale, bias, folded BN)
   float* ep_add = ep_mul + N;
+  // epilogue transpose staging: [4 warps][32 rows][EC floats], 16-byte chunks XOR-swizzled by the row
+  constexpr int EC = (N == 256) ? 16 : 32;
+  unsigned char* epi_stage =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ep_add + N) + 127) & ~(uintptr_t)127);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -356,7 +381,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       mbar_init(smem_u32(b_ab_empty + s), 1);
     }
     for (int s = 0; s < XS; ++s) {
-      mbar_init(smem_u32(b_x_full + s), N_XLOAD * 32);  // every loader thread: cp.async.mbarrier.arrive.noinc
+      mbar_init(smem_u32(b_x_full + s), W_PROD * 32 + 1);  // every producer thread (cp.async.mbarrier.arrive.noinc)
+                                                           // + thread 0 once more (expect_tx of the TMA loads)
       mbar_init(smem_u32(b_x_empty + s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -384,48 +410,19 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= W_XLOAD && warp < W_XLOAD + N_XLOAD) {
-    // ------------------------------------------------------------ halo loaders (2 warps) + tile metadata
-    const int lt = tid - W_XLOAD * 32;   // 0..63
-    const int q = lt & 7, rg = lt >> 3;   // 8 lanes x 16 B per 128-byte row, 8 rows per pass
-    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    auto fetch_meta = [&](int it2) {      // one thread: cp.async.bulk of the tile's metadata blob
-      const int pat = (blockIdx.x + it2 * gridDim.x) % p.P;
-      const int m2 = it2 & 1;
-      mbar_wait_relaxed(smem_u32(b_m_empty + m2), ((it2 >> 1) & 1) ^ 1, abort_flag, p.status, 1);
-      const int mbytes = p.meta_bytes[pat];
-      mbar_arrive_expect_tx(smem_u32(b_m_full + m2), mbytes);
-      bulk_g2s(smem_u32(meta_s + (size_t)m2 * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
-               smem_u32(b_m_full + m2));
-    };
-    if (lt == 0 && my_tiles > 0) fetch_meta(0);
-    uint32_t g = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int b = tile / p.P;
-      const int m = it & 1;
-      mbar_wait_relaxed(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 2);
-      const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
-      const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
-      const int h2 = p.plain ? TILE_M : hdr->h2;  // plain GEMM: only the tile's own rows are staged
-      const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);
-      const long long mesh_row0 = (long long)b * p.V;
-      for (int c = 0; c < n_chunk; ++c, ++g) {
-        const int xs = g % XS;
-        mbar_wait_relaxed(smem_u32(b_x_empty + xs), ((g / XS) & 1) ^ 1, abort_flag, p.status, 3);
-        const uint32_t dst0 = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
-        const float* src0 = p.x + c * FC + q * 4;
-        for (int i = rg; i < h2; i += 8) {
-          const int v = halo[i];
-          if (v >= 0) {
-            long long r = mesh_row0 + v;
-            if (p.in_unpool) r >>= 1;
-            cp_async16(dst0 + i * 128, src0 + r * p.fin);
-          } else {
-            sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
-          }
-        }
-        cp_async_arrive_noinc(smem_u32(b_x_full + xs));
-        if (c == 0 && lt == 0 && it + 1 < my_tiles) fetch_meta(it + 1);  // overlaps this tile's main loop
+    // ------------------------------------------------------------ tile-metadata loader (one thread, cp.async.bulk)
+    // (the X / T1 rows themselves are staged by the producers: two dedicated loader warps could not keep up once the
+    //  first sparse product moved out of this kernel — 16 spinning producer warps starve them of issue slots)
+    if (tid == W_XLOAD * 32) {
+      const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int pat = (blockIdx.x + it * gridDim.x) % p.P;
+        const int m = it & 1;
+        mbar_wait_relaxed(smem_u32(b_m_empty + m), ((it >> 1) & 1) ^ 1, abort_flag, p.status, 1);
+        const int mbytes = p.meta_bytes[pat];
+        mbar_arrive_expect_tx(smem_u32(b_m_full + m), mbytes);
+        bulk_g2s(smem_u32(meta_s + (size_t)m * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
+                 smem_u32(b_m_full + m));
       }
     }
   } else if (warp == W_BLOAD) {
@@ -480,20 +477,36 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       }
     }
   } else if (warp >= W_EPI0) {
-    // ------------------------------------------------------------ epilogue: TMEM -> registers -> HBM
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> (transpose) -> HBM
+    // tcgen05.ld hands every thread one accumulator ROW; storing that directly makes each warp-wide 16-byte store
+    // touch 32 different lines.  The rows are therefore transposed through a small per-warp staging buffer so that
+    // a warp-wide access covers whole 128-byte (N = 256: 64-byte) row pieces of a few rows; the fused epilogue
+    // (affine, ReLU, residual) runs in the transposed layout, where the residual reads coalesce as well.
     const int lane_base = (warp & 3) * 32;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int row_in_tile = lane_base + lane;
+    constexpr int CPR = EC / 4;             // 16-byte chunks per staged row
+    constexpr int RPI = 32 / CPR;           // rows covered by one warp-wide 16-byte access
+    const uint32_t stg = smem_u32(epi_stage) + (uint32_t)(warp - W_EPI0) * (32 * EC * 4);
+    const int prow = lane / CPR, pc = lane % CPR;
+    const uint32_t sw1 = (EC == 32) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
     int it = 0;
     int etn = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.P, pat = tile - b * p.P;
       const int as = it & 1;
-      const int n_rows = min(TILE_M, p.V - pat * TILE_M);
-      const long long r = (long long)b * p.V + (long long)pat * TILE_M + row_in_tile;
-      const bool valid = row_in_tile < n_rows;
-      float* yrow = p.y + r * p.ldy + p.y_col0;
-      const float* res_row = nullptr;
-      if (p.ep.res != nullptr) res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
+      const int n_valid = min(TILE_M, p.V - pat * TILE_M) - lane_base;  // rows of this warp's 32 that exist
+      const long long row0g = (long long)b * p.V + (long long)pat * TILE_M + lane_base;
+      if (p.ep.res != nullptr) {
+        // pull this tile's residual rows into L2 while its main loop is still running: the reads below then pay
+        // an L2 hit instead of a DRAM round trip per batch
+        const int lpr = (p.ep.res_F * 4 + 127) >> 7;  // 128-byte lines per residual row
+        for (int j = lane; j < 32 * lpr; j += 32) {
+          const int rr = j / lpr, ln = j - rr * lpr;
+          if (rr < n_valid) {
+            const long long r = row0g + rr;
+            prefetch_l2(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + ln * 32);
+          }
+        }
+      }
       mbar_wait_relaxed(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 1);
       tc_fence_after();
@@ -501,31 +514,65 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       for (int cb = 0; cb < N; cb += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * N + cb), v);
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = cb + j;
-            float o[4];
+        for (int h = 0; h < 32 / EC; ++h) {
+          // phase 1: lane = row
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = fmaf(__uint_as_float(v[j + e]), ep_mul[n + e], ep_add[n + e]);
-              if (p.ep.relu) t = fmaxf(t, 0.f);
-              o[e] = t;
+          for (int c = 0; c < CPR; ++c)
+            sts_f4(stg + lane * (EC * 4) + (((uint32_t)c ^ sw1) << 4),
+                   make_float4(__uint_as_float(v[h * EC + 4 * c]), __uint_as_float(v[h * EC + 4 * c + 1]),
+                               __uint_as_float(v[h * EC + 4 * c + 2]), __uint_as_float(v[h * EC + 4 * c + 3])));
+          __syncwarp();
+          // phase 2: lane = (row inside an RPI-row group, 16-byte chunk).  The residual pieces of the whole slice
+          // are fetched up front (read-only path): behind the y stores the compiler could not batch them.
+          constexpr int IB = 4;  // row groups per batch (bounds the registers held by the residual pieces)
+#pragma unroll
+          for (int i0 = 0; i0 < 32 / RPI; i0 += IB) {
+          float4 rv[IB];
+          if (p.ep.res != nullptr && p.res_identity) {
+#pragma unroll
+            for (int i = 0; i < IB; ++i) {
+              const int rr = (i0 + i) * RPI + prow;
+              const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+              const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
+              const long long r = row0g + rr;
+              rv[i] = (rr < n_valid)
+                          ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + n))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (res_row != nullptr) {
-              if (p.res_identity) {
-                const float4 rv = *reinterpret_cast<const float4*>(res_row + n);
-                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-              } else {
+          }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float l = p.ep.lam[n + e];
-                  o[e] += (1.f - l) * res_row[p.ep.i0[n + e]] + l * res_row[p.ep.i1[n + e]];
+          for (int i = 0; i < IB; ++i) {
+            const int rr = (i0 + i) * RPI + prow;
+            const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+            const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
+            const float4 a = lds_f4(stg + rr * (EC * 4) + (pc << 4));
+            if (rr < n_valid) {
+              const float4 mu = *reinterpret_cast<const float4*>(ep_mul + n);
+              const float4 ad = *reinterpret_cast<const float4*>(ep_add + n);
+              float o[4] = {fmaf(a.x, mu.x, ad.x), fmaf(a.y, mu.y, ad.y), fmaf(a.z, mu.z, ad.z), fmaf(a.w, mu.w, ad.w)};
+              if (p.ep.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+              }
+              const long long r = row0g + rr;
+              if (p.ep.res != nullptr) {
+                if (p.res_identity) {
+                  o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
+                } else {
+                  const float* res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float l = __ldg(p.ep.lam + n + e);
+                    o[e] += (1.f - l) * __ldg(res_row + __ldg(p.ep.i0 + n + e)) + l * __ldg(res_row + __ldg(p.ep.i1 + n + e));
+                  }
                 }
               }
+              *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + n) = make_float4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<float4*>(yrow + n) = make_float4(o[0], o[1], o[2], o[3]);
           }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -547,11 +594,69 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
     uint32_t t1_row[T1_ROWS], t1_e[T1_ROWS];
     uint32_t row0 = 0, row1 = 0, r0e = 0, r1e = 0, ent_a = 0;
     int ptn = 0;
+
+    // Stage flat stage g2 (tile it2, chunk c2) into Xs[g2 % XS] (and T1s[g2 % XS] when T1 is given): 16-byte
+    // cp.async copies, 8 lanes per 128-byte row, four rows per thread in flight; completion is signalled on
+    // x_full[g2 % XS] by cp.async.mbarrier.arrive.noinc.  The target stage was last read in stage g2 - XS, whose
+    // end barrier every producer has passed before it gets here.
+    auto issue_stage = [&](int g2) {
+      const int it2 = g2 / n_chunk, c2 = g2 - it2 * n_chunk;
+      const int tile2 = blockIdx.x + it2 * gridDim.x;
+      const int b2 = tile2 / p.P;
+      const int m2 = it2 & 1;
+      if (c2 == 0) mbar_wait(smem_u32(b_m_full + m2), (it2 >> 1) & 1, abort_flag, p.status, 8);
+      const unsigned char* mb2 = meta_s + (size_t)m2 * p.meta_stride;
+      const TileHeader* hdr2 = reinterpret_cast<const TileHeader*>(mb2);
+      const int* halo = reinterpret_cast<const int*>(mb2 + hdr2->off_halo);
+      const long long mesh_row0 = (long long)b2 * p.V;
+      const int xs2 = g2 % XS;
+      auto stage_rows = [&](uint32_t dbase, const float* sbase, int first, int n_rows, bool unpool) {
+        for (int i0 = first + rg; i0 < n_rows; i0 += 256) {
+          int v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (i0 + 64 * u < n_rows) ? halo[i0 + 64 * u] : -2;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 64 * u;
+            if (v[u] >= 0) {
+              long long r = mesh_row0 + v[u];
+              if (unpool) r >>= 1;
+              cp_async16(dbase + i * 128, sbase + r * p.fin);
+            } else if (v[u] == -1) {
+              sts_f4(dbase + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+          }
+        }
+      };
+      const uint32_t xbar = smem_u32(b_x_full + xs2);
+      if (p.tma) {
+        // own rows: one TMA box per operand, issued by one thread and landing asynchronously (the cp.async route
+        // blocks the issuing warps once the load queue is full, i.e. for most of the copy)
+        if (tid == 0) {
+          const int own0 = tile2 * TILE_M;  // V is a multiple of 128 here: tiles never straddle meshes
+          mbar_arrive_expect_tx(xbar, (p.in_unpool ? TILE_M / 2 : TILE_M) * 128 + (t1g ? TILE_M * 128 : 0));
+          tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
+          if (t1g) tma_load_2d(smem_u32(T1s + xs2 * t1_stage_floats), &p.tm_t1, c2 * FC, own0, xbar);
+        }
+        if (t1g)
+          stage_rows(smem_u32(T1s + xs2 * t1_stage_floats) + q * 16, p.t1 + c2 * FC + q * 4, TILE_M, hdr2->h1, false);
+      } else {
+        if (t1g)
+          stage_rows(smem_u32(T1s + xs2 * t1_stage_floats) + q * 16, p.t1 + c2 * FC + q * 4, 0, hdr2->h1, false);
+        stage_rows(smem_u32(Xs + xs2 * xs_stage_floats) + q * 16, p.x + c2 * FC + q * 4, 0,
+                   (p.plain || t1g) ? TILE_M : hdr2->h2, p.in_unpool != 0);
+        if (tid == 0) mbar_arrive(xbar);
+      }
+      cp_async_arrive_noinc(xbar);
+    };
+
+    const int xsh = (p.tma && p.in_unpool) ? 1 : 0;  // TMA-staged unpooled input: staged row = tile row >> 1
+    if (n_stage > 0) issue_stage(0);
     for (int g = 0; g < n_stage; ++g) {
       const int it = g / n_chunk, c = g - it * n_chunk;
       const int m = it & 1;
       const int xs = g % XS;
-      if (c == 0) mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 8);
+      if (XS == 2 && g + 1 < n_stage) issue_stage(g + 1);  // prefetch: overlaps this stage's work
       if (tid == 0) trace_ev(p, 0, ptn, 1);
       mbar_wait(smem_u32(b_x_full + xs), (g / XS) & 1, abort_flag, p.status, 9);
       if (tid == 0) trace_ev(p, 0, ptn, 2);
@@ -562,7 +667,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
         const uint32_t mb_a = smem_u32(mb);
         const uint32_t rp_a = mb_a + hdr->off_rp, ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
         ent_a = mb_a + hdr->off_ent;
-        const int h1 = hdr->h1;
+        const int h1 = (t1g || p.plain) ? 0 : hdr->h1;  // the trimmed metadata has no T1 row order
 #pragma unroll
         for (int t = 0; t < T1_ROWS; ++t) {
           const int j = rg + 64 * t;
@@ -579,7 +684,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
         r1e = lds_u16(rp_a + 2 * row1) | (lds_u16(rp_a + 2 * row1 + 2) << 16);
       }
       const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
-      const uint32_t t1s_q = t1s_a + q * 16;
+      const uint32_t t1s_q = t1s_a + (t1g ? (uint32_t)(xs * t1_stage_floats * 4) : 0u) + q * 16;
       if (p.plain) {
         // plain GEMM: the staged rows ARE the A operand (scaled into fp16 range if a_scale is given)
         const int s = ucnt % NS;
@@ -588,7 +693,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           const uint32_t i = ps * 64 + rg;
-          float4 v = lds_f4(xs_q + i * 128);
+          float4 v = lds_f4(xs_q + (i >> xsh) * 128);
           v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
           uint2 hi, lo;
           split4(v, hi, lo);
@@ -601,29 +706,29 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
         if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
         ++ucnt;
         producer_barrier();
-        if (tid == 0) {
-          mbar_arrive(smem_u32(b_x_empty + xs));
-          if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-        }
+        if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+        if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1);  // single stage: refill only after everybody is done
         continue;
       }
       // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows); two rows per
       //     thread are gathered together for memory-level parallelism.
+      if (!t1g) {
 #pragma unroll
-      for (int t = 0; t < T1_ROWS; ++t) {
-        if (t1_row[t] != 0xFFFFu)
-          sts_f4(t1s_q + t1_row[t] * 128, gather_row4(ent_a, t1_e[t] & 0xFFFFu, t1_e[t] >> 16, xs_q));
+        for (int t = 0; t < T1_ROWS; ++t) {
+          if (t1_row[t] != 0xFFFFu)
+            sts_f4(t1s_q + t1_row[t] * 128, gather_row4(ent_a, t1_e[t] & 0xFFFFu, t1_e[t] >> 16, xs_q));
+        }
+        if (tid == 0) trace_ev(p, 0, ptn, 4);
+        producer_barrier();
+        if (tid == 0) trace_ev(p, 0, ptn, 5);
       }
-      if (tid == 0) trace_ev(p, 0, ptn, 4);
-      producer_barrier();
-      if (tid == 0) trace_ev(p, 0, ptn, 5);
       // (2) T2 = 2 L~ T1 - X on the two tile rows this thread finishes
       float4 tv[3][2];
       {
         const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
         const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
-        tv[0][0] = lds_f4(xs_q + row0 * 128);
-        tv[0][1] = lds_f4(xs_q + row1 * 128);
+        tv[0][0] = lds_f4(xs_q + (row0 >> xsh) * 128);
+        tv[0][1] = lds_f4(xs_q + (row1 >> xsh) * 128);
         tv[1][0] = lds_f4(t1s_q + row0 * 128);
         tv[1][1] = lds_f4(t1s_q + row1 * 128);
         const float4 a = tv[0][0], c2 = tv[0][1];
@@ -671,10 +776,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const KParam
       if (tid == 0) trace_ev(p, 0, ptn, 7);
       producer_barrier();  // everybody is done with Xs[xs] and T1s
       if (tid == 0) trace_ev(p, 0, ptn, 8);
-      if (tid == 0) {
-        mbar_arrive(smem_u32(b_x_empty + xs));
-        if (c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-      }
+      if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+      if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1);  // single stage: refill only after everybody is done
     }
   }
   tc_fence_before();
@@ -989,6 +1092,90 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
   if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================
+// k_cheb_t1 — T1 = L~ X for every row, written once to HBM (fp32, logical rows).  With it the conv kernel only
+// needs the tile's own X rows and the T1 rows of its 1-hop halo: the 35 % of the first sparse product that the
+// fused kernel spends re-computing T1 on halo rows disappears, and so does its 2-hop X staging.
+// Simple kernel: one CTA (512 threads, ~60 KB shared memory -> 3 CTAs per SM) per 128-row tile; the 1-hop halo of
+// X is staged chunk by chunk with double-buffered cp.async, the gather runs out of shared memory.
+// =====================================================================================
+struct T1Params {
+  const float* x;
+  int in_unpool;
+  int V, P, fin;
+  const unsigned char* meta;
+  const int* meta_bytes;
+  int meta_stride, max_h1;
+  float* t1;
+};
+
+__global__ void __launch_bounds__(512, 2) k_cheb_t1(const T1Params p) {
+  extern __shared__ __align__(16) unsigned char smem_t1[];
+  unsigned char* meta_s = smem_t1;
+  float* Xs = reinterpret_cast<float*>(smem_t1 + p.meta_stride);  // [2][max_h1][32]
+  const size_t stage_floats = (size_t)p.max_h1 * FC;
+  const int tid = threadIdx.x, q = tid & 7, rg = tid >> 3;
+  const int tile = blockIdx.x;
+  const int b = tile / p.P, pat = tile - b * p.P;
+  const long long mesh_row0 = (long long)b * p.V;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.meta + (size_t)pat * p.meta_stride);
+    uint4* dst = reinterpret_cast<uint4*>(meta_s);
+    const int n16 = p.meta_bytes[pat] >> 4;
+    for (int i = tid; i < n16; i += 512) dst[i] = src[i];
+  }
+  __syncthreads();
+  const TileHeader* hdr = reinterpret_cast<const TileHeader*>(meta_s);
+  const int h1 = hdr->h1;
+  const int* halo = reinterpret_cast<const int*>(meta_s + hdr->off_halo);
+  const uint32_t mb_a = smem_u32(meta_s);
+  const uint32_t rp_a = mb_a + hdr->off_rp, ent_a = mb_a + hdr->off_ent;
+  const int n_chunk = p.fin / FC;
+  auto stage = [&](int c, int buf) {
+    const uint32_t dst0 = smem_u32(Xs + buf * stage_floats) + q * 16;
+    const float* src0 = p.x + c * FC + q * 4;
+    for (int i = rg; i < h1; i += 64) {
+      const int v = halo[i];
+      if (v >= 0) {
+        long long r = mesh_row0 + v;
+        if (p.in_unpool) r >>= 1;
+        cp_async16(dst0 + i * 128, src0 + r * p.fin);
+      } else {
+        sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // rows this thread produces (same for every chunk)
+  int vtx[2];
+  uint32_t re[2];
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int i = ps * 64 + rg;
+    vtx[ps] = halo[i];
+    re[ps] = lds_u16(rp_a + 2 * i) | (lds_u16(rp_a + 2 * i + 2) << 16);
+  }
+  stage(0, 0);
+  for (int c = 0; c < n_chunk; ++c) {
+    if (c + 1 < n_chunk) {
+      stage(c + 1, (c + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t xs_q = smem_u32(Xs + (c & 1) * stage_floats) + q * 16;
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      if (vtx[ps] >= 0) {
+        const float4 acc = gather_row4(ent_a, re[ps] & 0xFFFFu, re[ps] >> 16, xs_q);
+        *reinterpret_cast<float4*>(p.t1 + (mesh_row0 + vtx[ps]) * p.fin + c * FC + q * 4) = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // fp32 reference-layout weights [Fout, Fin*3] (column = f*3+k) -> K-blocks of fp16 [Whi | Wlo]
 // in the exact shared-memory image (128B-swizzled), block u = chunk*3 + k, so the kernel can
 // fetch a block with a single cp.async.bulk.
@@ -1014,10 +1201,18 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
 }
 
 long long* g_umma_trace = nullptr;  // debug: set through set_umma_trace()
+// debug: P2M_UMMA_TMA=0 stages every row with cp.async (A/B measurements of the TMA own-row loads)
+const bool g_umma_tma = [] { const char* e = std::getenv("P2M_UMMA_TMA"); return !(e && e[0] == '0'); }();
 
-size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g) {
-  return 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +
-         2 * (size_t)g.meta_stride + 8 * (2 * NS + 2 * XS + 8) + 16 + 2 * (size_t)N * 4 + 16;
+// mode: 0 = fused (X with its 2-hop halo staged, T1 recomputed on chip), 1 = T1 given, 2 = plain GEMM
+inline int epi_stage_bytes(int N) { return 4 * 32 * (N == 256 ? 16 : 32) * 4; }  // per-warp transpose staging
+size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g, int mode = 0) {
+  const size_t fixed = 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + 8 * (2 * NS + 2 * XS + 8) + 16 +
+                       2 * (size_t)N * 4 + 16 + 128 + (size_t)epi_stage_bytes(N);
+  if (mode == 1)
+    return fixed + (size_t)XS * TILE_M * FC * 4 + (size_t)XS * g.max_h1 * FC * 4 + 2 * (size_t)g.meta1_stride;
+  if (mode == 2) return fixed + (size_t)XS * TILE_M * FC * 4 + 2 * (size_t)g.meta1_stride;
+  return fixed + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 + 2 * (size_t)g.meta_stride;
 }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 inline int ring_stages(int N) { return N == 256 ? 2 : 3; }
@@ -1026,10 +1221,39 @@ inline int x_stages(int N, const DevLevel& g) {
   return smem_bytes_for(N, ring_stages(N), 2, g) <= SMEM_LIMIT ? 2 : 1;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<TmapEncodeFn>(f);
+  }();
+  return fn;
+}
+// [rows, fin] fp32 row-major matrix, box = 32 features x box_rows rows, dense (unswizzled) 128-byte rows in shared memory
+bool make_row_tmap(CUtensorMap* tm, const float* base, long long rows, int fin, int box_rows) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (enc == nullptr || (reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)fin, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)fin * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)FC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int N, int NS, int XS>
 int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   const DevLevel& g = *a.g;
-  const size_t smem = smem_bytes_for(N, NS, XS, g);
+  const int mode = a.plain ? 2 : (a.t1 != nullptr ? 1 : 0);
+  const size_t smem = smem_bytes_for(N, NS, XS, g, mode);
   auto kern = k_cheb_conv_umma<N, NS, XS>;
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KParams p;
@@ -1039,9 +1263,9 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.P = g.n_pattern;
   p.fin = a.fin;
   p.n_tiles = a.batch * g.n_pattern;
-  p.meta = g.tile_meta;
-  p.meta_bytes = g.tile_meta_bytes;
-  p.meta_stride = g.meta_stride;
+  p.meta = mode ? g.tile_meta1 : g.tile_meta;
+  p.meta_bytes = mode ? g.tile_meta1_bytes : g.tile_meta_bytes;
+  p.meta_stride = mode ? g.meta1_stride : g.meta_stride;
   p.max_h1 = g.max_h1;
   p.max_h2 = g.max_h2;
   p.wpack = static_cast<const unsigned char*>(a.wpack);
@@ -1049,12 +1273,22 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.ep = to_dev(a.ep);
   p.res_identity = (a.ep.res != nullptr && a.ep.res_F == a.fout) ? 1 : 0;
   p.y = a.y;
+  p.t1 = a.t1;
   p.plain = a.plain;
   p.a_scale = a.a_scale;
   p.ldy = a.ldy > 0 ? a.ldy : a.fout;
   p.y_col0 = a.y_col0;
   p.status = status;
   p.trace = g_umma_trace;
+  p.tma = 0;
+  std::memset(&p.tm_x, 0, sizeof(p.tm_x));
+  std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
+  if ((a.t1 != nullptr || a.plain) && g.V % TILE_M == 0 && g_umma_tma) {
+    const long long rows = (long long)a.batch * g.V;
+    bool ok = make_row_tmap(&p.tm_x, a.x, a.in_unpool ? rows / 2 : rows, a.fin, a.in_unpool ? TILE_M / 2 : TILE_M);
+    if (ok && a.t1 != nullptr) ok = make_row_tmap(&p.tm_t1, a.t1, rows, a.fin, TILE_M);
+    p.tma = ok ? 1 : 0;
+  }
   const int grid = std::min(p.n_tiles, sm_count);
   kern<<<grid, NUM_THREADS2, smem, s>>>(p);
   P2M_LAUNCH_OK();
@@ -1064,6 +1298,11 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
 template <int N>
 int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   constexpr int NS = (N == 256) ? 2 : 3;
+  if (a.t1 != nullptr || a.plain) {
+    if (smem_bytes_for(N, NS, 2, *a.g, a.plain ? 2 : 1) <= SMEM_LIMIT)
+      return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
+    return launch_cfg<N, NS, 1>(a, status, zero_row, sm_count, s);
+  }
   if (x_stages(N, *a.g) == 2) return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
   return launch_cfg<N, NS, 1>(a, status, zero_row, sm_count, s);
 }
@@ -1076,8 +1315,8 @@ int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_c
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
                           std::vector<void*>* owned) {
   const int P = (V + TILE_M - 1) / TILE_M;
-  std::vector<std::vector<unsigned char>> blobs(P);
-  int max_h1 = 0, max_h2 = 0, stride = 0;
+  std::vector<std::vector<unsigned char>> blobs(P), blobs1(P);
+  int max_h1 = 0, max_h2 = 0, stride = 0, stride1 = 0;
   std::vector<int> slot_of(V, -1);
   for (int pt = 0; pt < P; ++pt) {
     const int v0 = pt * TILE_M;
@@ -1155,6 +1394,30 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
     max_h1 = std::max(max_h1, h1);
     max_h2 = std::max(max_h2, h2);
     stride = std::max(stride, off);
+    {
+      // trimmed variant: staged rows = own + 1-hop (h2 := h1), CSR rows of the 128 own rows (they come first in ent)
+      const int nnz1 = rp[TILE_M <= h1 ? TILE_M : h1];
+      TileHeader t{};
+      t.n_rows = n_rows;
+      t.h1 = h1;
+      t.h2 = h1;
+      t.nnz = nnz1;
+      int o1 = 64;
+      t.off_halo = o1; o1 += up16(h1 * 4);
+      t.off_rp = o1;   o1 += up16((TILE_M + 1) * 2);
+      t.off_ent = o1;  o1 += up16(nnz1 * 8);
+      t.off_ord2 = o1; o1 += up16(TILE_M * 2);
+      t.off_ord1 = t.off_ord2;  // not used by the consumers of this variant
+      t.bytes = o1;
+      std::vector<unsigned char>& b1 = blobs1[pt];
+      b1.assign(o1, 0);
+      std::memcpy(b1.data(), &t, sizeof(t));
+      std::memcpy(b1.data() + t.off_halo, halo.data(), h1 * 4);
+      std::memcpy(b1.data() + t.off_rp, rp.data(), (TILE_M + 1) * 2);
+      if (nnz1) std::memcpy(b1.data() + t.off_ent, ent.data(), (size_t)nnz1 * 8);
+      std::memcpy(b1.data() + t.off_ord2, ord2.data(), TILE_M * 2);
+      stride1 = std::max(stride1, o1);
+    }
     for (int v : halo)
       if (v >= 0) slot_of[v] = -1;
   }
@@ -1173,6 +1436,26 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
   owned->push_back(d_bytes);
   P2M_CUDA_OK(cudaMemcpy(d_meta, all.data(), all.size(), cudaMemcpyHostToDevice));
   P2M_CUDA_OK(cudaMemcpy(d_bytes, bytes.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  {
+    stride1 = (stride1 + 127) & ~127;
+    std::vector<unsigned char> all1((size_t)P * stride1, 0);
+    std::vector<int> bytes1(P);
+    for (int pt = 0; pt < P; ++pt) {
+      std::memcpy(all1.data() + (size_t)pt * stride1, blobs1[pt].data(), blobs1[pt].size());
+      bytes1[pt] = (int)blobs1[pt].size();
+    }
+    unsigned char* d_meta1 = nullptr;
+    int* d_bytes1 = nullptr;
+    P2M_CUDA_OK(cudaMalloc(&d_meta1, all1.size()));
+    owned->push_back(d_meta1);
+    P2M_CUDA_OK(cudaMalloc(&d_bytes1, sizeof(int) * P));
+    owned->push_back(d_bytes1);
+    P2M_CUDA_OK(cudaMemcpy(d_meta1, all1.data(), all1.size(), cudaMemcpyHostToDevice));
+    P2M_CUDA_OK(cudaMemcpy(d_bytes1, bytes1.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+    out->tile_meta1 = d_meta1;
+    out->tile_meta1_bytes = d_bytes1;
+    out->meta1_stride = stride1;
+  }
   out->n_pattern = P;
   out->tile_meta = d_meta;
   out->tile_meta_bytes = d_bytes;
@@ -1235,6 +1518,29 @@ int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, 
       P2M_LAUNCH_OK();
     }
   }
+  return P2M_OK;
+}
+
+int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s) {
+  if (g.tile_meta == nullptr || fin % FC != 0) {
+    set_error("cheb_t1: unsupported shape");
+    return P2M_ERR_INVALID;
+  }
+  const size_t smem = (size_t)g.meta1_stride + 2 * (size_t)g.max_h1 * FC * 4 + 16;
+  P2M_CUDA_OK(cudaFuncSetAttribute(k_cheb_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  T1Params p;
+  p.x = x;
+  p.in_unpool = in_unpool;
+  p.V = g.V;
+  p.P = g.n_pattern;
+  p.fin = fin;
+  p.meta = g.tile_meta1;
+  p.meta_bytes = g.tile_meta1_bytes;
+  p.meta_stride = g.meta1_stride;
+  p.max_h1 = g.max_h1;
+  p.t1 = t1;
+  k_cheb_t1<<<batch * g.n_pattern, 512, smem, s>>>(p);
+  P2M_LAUNCH_OK();
   return P2M_OK;
 }
 

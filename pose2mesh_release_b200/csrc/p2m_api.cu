@@ -51,6 +51,7 @@ struct p2m_model {
   int* out_map = nullptr;        // optional fused output gather (vertex -> slot, -1 = dropped)
   int out_rows = 0;
   float* zero_row = nullptr;     // 128 B of zeros (halo source for the empty slots of ragged tiles)
+  int split_t1 = 1;              // tcgen05 conv: T1 = L~x in a separate pass (k_cheb_t1) instead of on-chip halo recompute
   int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
   std::vector<cudaEvent_t> ev_beg, ev_end;
   std::vector<void*> owned;  // device allocations to free
@@ -239,6 +240,10 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
   if (m->precision == P2M_PREC_FP16X3_TC && wpack != nullptr && umma_conv_supported(g, L.fin, L.fout)) {
     P2M_TRY(launch_umma_pack_weights(w_ref, L.fin, L.fout, wpack, s));
     UmmaConvArgs a;
+    if (m->split_t1 && T != nullptr) {  // first sparse product as its own pass (T doubles as the T1 buffer)
+      P2M_TRY(launch_cheb_t1(g, x, in_unpool, B, L.fin, T, s));
+      a.t1 = T;
+    }
     a.g = &g;
     a.x = x;
     a.in_unpool = in_unpool;
@@ -464,6 +469,13 @@ int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out) {
 // Debug: route the tcgen05 kernel's CTA-0 event log into `dev_buf` (device, 8*512 int64) or disable (NULL).
 int p2m_debug_set_trace(void* dev_buf) {
   set_umma_trace(static_cast<long long*>(dev_buf));
+  return P2M_OK;
+}
+
+// Debug / ablation: 1 (default) = two-pass tcgen05 conv (k_cheb_t1 + conv with given T1), 0 = fully fused conv.
+int p2m_debug_set_split_t1(p2m_model_t* m, int enable) {
+  if (!m) return P2M_ERR_INVALID;
+  m->split_t1 = enable ? 1 : 0;
   return P2M_OK;
 }
 

@@ -56,6 +56,11 @@ struct DevLevel {
   const unsigned char* tile_meta = nullptr;   // [n_pattern][meta_stride]
   const int* tile_meta_bytes = nullptr;       // [n_pattern] bytes to copy (multiple of 16)
   int meta_stride = 0;
+  // trimmed blobs for the kernels that get X / T1 rows instead of recomputing them (k_cheb_t1, conv with T1 given):
+  // halo list up to the 1-hop rows and the CSR rows of the tile's own 128 rows only
+  const unsigned char* tile_meta1 = nullptr;  // [n_pattern][meta1_stride]
+  const int* tile_meta1_bytes = nullptr;
+  int meta1_stride = 0;
   int max_h1 = 0, max_h2 = 0;
 };
 
@@ -180,6 +185,7 @@ struct UmmaConvArgs {
   float* y;                 // [rows, fout]
   // plain-GEMM mode (backward dT = dz * W_k): no SpMM, x is [rows, fin] and the K-blocks come from
   // launch_umma_pack_plain; y is written at y[r*ldy + y_col0 + n]
+  const float* t1 = nullptr;        // optional precomputed T1 = L~ x [rows, fin] (launch_cheb_t1)
   int plain = 0;
   const float* a_scale = nullptr;   // device scalar from launch_absmax_scale (or null)
   long long ldy = 0;                // 0: fout
@@ -201,6 +207,8 @@ int launch_absmax_scale(const float* x, long long n, float* scale_out, cudaStrea
 bool umma_dw_supported(const DevLevel& g, int fin, int fout);
 int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout, const float* dz,
                    const float* a_scale, float* dw_ref, int* status, int sm_count, cudaStream_t s);
+// T1 = L~ x for all rows of a level (tile-staged gather), t1 [batch*V, fin] fp32
+int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s);
 int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
 
 }  // namespace p2m
