@@ -1096,8 +1096,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
 // k_cheb_t1 — T1 = L~ X for every row, written once to HBM (fp32, logical rows).  With it the conv kernel only
 // needs the tile's own X rows and the T1 rows of its 1-hop halo: the 35 % of the first sparse product that the
 // fused kernel spends re-computing T1 on halo rows disappears, and so does its 2-hop X staging.
-// Simple kernel: one CTA (512 threads, ~60 KB shared memory -> 3 CTAs per SM) per 128-row tile; the 1-hop halo of
-// X is staged chunk by chunk with double-buffered cp.async, the gather runs out of shared memory.
+// Simple kernel: one CTA (512 threads, two per SM) per 128-row tile; the 1-hop halo of X is staged chunk by chunk
+// through a 4-deep cp.async ring (one barrier per chunk), the gather runs out of shared memory.
 // =====================================================================================
 struct T1Params {
   const float* x;
@@ -1109,10 +1109,12 @@ struct T1Params {
   float* t1;
 };
 
+// T1_STAGES = cp.async ring depth (chunks in flight per CTA): 4 when two CTAs of that size fit an SM, else 3 or 2
+template <int T1_STAGES>
 __global__ void __launch_bounds__(512, 2) k_cheb_t1(const T1Params p) {
   extern __shared__ __align__(16) unsigned char smem_t1[];
   unsigned char* meta_s = smem_t1;
-  float* Xs = reinterpret_cast<float*>(smem_t1 + p.meta_stride);  // [2][max_h1][32]
+  float* Xs = reinterpret_cast<float*>(smem_t1 + p.meta_stride);  // [T1_STAGES][max_h1][32]
   const size_t stage_floats = (size_t)p.max_h1 * FC;
   const int tid = threadIdx.x, q = tid & 7, rg = tid >> 3;
   const int tile = blockIdx.x;
@@ -1129,42 +1131,49 @@ __global__ void __launch_bounds__(512, 2) k_cheb_t1(const T1Params p) {
   const int h1 = hdr->h1;
   const int* halo = reinterpret_cast<const int*>(meta_s + hdr->off_halo);
   const uint32_t mb_a = smem_u32(meta_s);
-  const uint32_t rp_a = mb_a + hdr->off_rp, ent_a = mb_a + hdr->off_ent;
+  const uint32_t rp_a = mb_a + hdr->off_rp, ent_a = mb_a + hdr->off_ent, ord2_a = mb_a + hdr->off_ord2;
   const int n_chunk = p.fin / FC;
-  auto stage = [&](int c, int buf) {
-    const uint32_t dst0 = smem_u32(Xs + buf * stage_floats) + q * 16;
-    const float* src0 = p.x + c * FC + q * 4;
-    for (int i = rg; i < h1; i += 64) {
-      const int v = halo[i];
-      if (v >= 0) {
-        long long r = mesh_row0 + v;
-        if (p.in_unpool) r >>= 1;
-        cp_async16(dst0 + i * 128, src0 + r * p.fin);
-      } else {
-        sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+  // source rows of the staged slots this thread copies (same for every chunk): slots rg, rg + 64, ...
+  long long srow[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = rg + 64 * u;
+    const int v = (i < h1) ? halo[i] : -2;
+    long long r = mesh_row0 + v;
+    if (p.in_unpool) r >>= 1;
+    srow[u] = (v >= 0) ? r * p.fin : (long long)v;  // -1: empty slot (zero-filled), -2: beyond the halo
+  }
+  auto stage = [&](int c) {
+    if (c < n_chunk) {
+      const uint32_t dst0 = smem_u32(Xs + (c % T1_STAGES) * stage_floats) + q * 16;
+      const float* src0 = p.x + c * FC + q * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = rg + 64 * u;
+        if (srow[u] >= 0)
+          cp_async16(dst0 + i * 128, src0 + srow[u]);
+        else if (srow[u] == -1)
+          sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (possibly empty: keeps the group count uniform)
   };
-  // rows this thread produces (same for every chunk)
+  // rows this thread produces, taken in length-sorted order: the four rows of a warp then have similar lengths
   int vtx[2];
   uint32_t re[2];
 #pragma unroll
   for (int ps = 0; ps < 2; ++ps) {
-    const int i = ps * 64 + rg;
+    const int i = lds_u16(ord2_a + 2 * (ps * 64 + rg));
     vtx[ps] = halo[i];
     re[ps] = lds_u16(rp_a + 2 * i) | (lds_u16(rp_a + 2 * i + 2) << 16);
   }
-  stage(0, 0);
+#pragma unroll
+  for (int c = 0; c < T1_STAGES - 1; ++c) stage(c);
   for (int c = 0; c < n_chunk; ++c) {
-    if (c + 1 < n_chunk) {
-      stage(c + 1, (c + 1) & 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t xs_q = smem_u32(Xs + (c & 1) * stage_floats) + q * 16;
+    asm volatile("cp.async.wait_group %0;" ::"n"(T1_STAGES - 2) : "memory");  // chunk c has landed (this thread's part)
+    __syncthreads();  // ... and everybody's; also: everybody is done with chunk c - 1, whose stage is refilled next
+    stage(c + T1_STAGES - 1);
+    const uint32_t xs_q = smem_u32(Xs + (c % T1_STAGES) * stage_floats) + q * 16;
 #pragma unroll
     for (int ps = 0; ps < 2; ++ps) {
       if (vtx[ps] >= 0) {
@@ -1172,7 +1181,6 @@ __global__ void __launch_bounds__(512, 2) k_cheb_t1(const T1Params p) {
         *reinterpret_cast<float4*>(p.t1 + (mesh_row0 + vtx[ps]) * p.fin + c * FC + q * 4) = acc;
       }
     }
-    __syncthreads();
   }
 }
 
@@ -1526,8 +1534,16 @@ int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, 
     set_error("cheb_t1: unsupported shape");
     return P2M_ERR_INVALID;
   }
-  const size_t smem = (size_t)g.meta1_stride + 2 * (size_t)g.max_h1 * FC * 4 + 16;
-  P2M_CUDA_OK(cudaFuncSetAttribute(k_cheb_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (g.max_h1 > 256) {  // 4 staged slots per row group
+    set_error("cheb_t1: halo too large");
+    return P2M_ERR_INVALID;
+  }
+  auto smem_for = [&](int stages) { return (size_t)g.meta1_stride + stages * (size_t)g.max_h1 * FC * 4 + 16; };
+  const size_t half_sm = (228 * 1024) / 2 - 1024;  // two CTAs per SM (1 KB per CTA is reserved by the system)
+  const int stages = smem_for(4) <= half_sm ? 4 : (smem_for(3) <= half_sm ? 3 : 2);
+  const size_t smem = smem_for(stages);
+  auto kern = stages == 4 ? k_cheb_t1<4> : (stages == 3 ? k_cheb_t1<3> : k_cheb_t1<2>);
+  P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   T1Params p;
   p.x = x;
   p.in_unpool = in_unpool;
@@ -1539,7 +1555,7 @@ int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, 
   p.meta_stride = g.meta1_stride;
   p.max_h1 = g.max_h1;
   p.t1 = t1;
-  k_cheb_t1<<<batch * g.n_pattern, 512, smem, s>>>(p);
+  kern<<<batch * g.n_pattern, 512, smem, s>>>(p);
   P2M_LAUNCH_OK();
   return P2M_OK;
 }
