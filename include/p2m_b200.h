@@ -91,6 +91,9 @@ int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out);
 int p2m_debug_set_trace(void* dev_buf);
 /* Debug / ablation: 1 (default) = T1 = L~x as a separate pass + conv with given T1; 0 = fully fused conv.   */
 int p2m_debug_set_split_t1(p2m_model_t* m, int enable);
+/* Debug / ablation: 1 (default) = in eval mode the 128->64 conv's epilogue produces the 64->3 head's projections
+ * itself (the 64-wide activation is never written); 0 = the two layers run separately.                         */
+int p2m_debug_set_fuse_head(p2m_model_t* m, int enable);
 
 /* Bytes of device workspace p2m_meshnet_forward needs for batch B.  In training mode the workspace
  * also carries what p2m_meshnet_backward reads, so it must stay alive and untouched in between.   */

@@ -311,6 +311,8 @@ struct KParams {
   float* y;
   int* status;
   long long* trace;  // optional [8][512] event log of CTA 0 (debug): (event << 48) | clock
+  const float* head_wt;  // optional fused thin head (N == 64): epilogue writes head_z[row][12] = y_row * head_wt[64][12]
+  float* head_z;
   int tma;           // 1: the tile's own rows of x (and t1) arrive by one 2-D TMA load each (T1-given / plain mode on
                      //    levels whose size is a multiple of 128); with in_unpool the x box is the 64 source rows
   CUtensorMap tm_x, tm_t1;
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
   constexpr int EC = (N == 256) ? 16 : 32;
   unsigned char* epi_stage =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ep_add + N) + 127) & ~(uintptr_t)127);
+  float* head_w_s = reinterpret_cast<float*>(epi_stage + 4 * 32 * EC * 4);  // [64][12] (N == 64 with a fused head)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -403,6 +406,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     ep_mul[n] = W_INV_SCALE * sc;
     ep_add[n] = fmaf(bi, p.ep.scale ? p.ep.scale[n] : 1.f, sh);
   }
+  if (N == 64 && p.head_z != nullptr)
+    for (int i = threadIdx.x; i < 64 * 12; i += NUM_THREADS2) head_w_s[i] = p.head_wt[i];
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -510,6 +515,36 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       mbar_wait_relaxed(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 1);
       tc_fence_after();
+      if (N == 64 && p.head_z != nullptr) {
+        // fused thin head: thread = row; y_n = act(acc_n * mul_n + add_n) never leaves the registers, only the
+        // 12 projections Z = y W' (W' = [W0 - W2 | W1 | W2] of the 64 -> 3 layer, 4-padded) are written
+        float z[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) z[j] = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < N; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * N + cb), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = cb + j;
+            float t = fmaf(__uint_as_float(v[j]), ep_mul[n], ep_add[n]);
+            if (p.ep.relu) t = fmaxf(t, 0.f);
+            const float4 w0 = *reinterpret_cast<const float4*>(head_w_s + n * 12);
+            const float4 w1 = *reinterpret_cast<const float4*>(head_w_s + n * 12 + 4);
+            const float4 w2 = *reinterpret_cast<const float4*>(head_w_s + n * 12 + 8);
+            z[0] = fmaf(t, w0.x, z[0]); z[1] = fmaf(t, w0.y, z[1]); z[2] = fmaf(t, w0.z, z[2]); z[3] = fmaf(t, w0.w, z[3]);
+            z[4] = fmaf(t, w1.x, z[4]); z[5] = fmaf(t, w1.y, z[5]); z[6] = fmaf(t, w1.z, z[6]); z[7] = fmaf(t, w1.w, z[7]);
+            z[8] = fmaf(t, w2.x, z[8]); z[9] = fmaf(t, w2.y, z[9]); z[10] = fmaf(t, w2.z, z[10]); z[11] = fmaf(t, w2.w, z[11]);
+          }
+        }
+        if (lane < n_valid) {
+          float4* zr = reinterpret_cast<float4*>(p.head_z + (row0g + lane) * 12);
+          zr[0] = make_float4(z[0], z[1], z[2], z[3]);
+          zr[1] = make_float4(z[4], z[5], z[6], z[7]);
+          zr[2] = make_float4(z[8], z[9], z[10], z[11]);
+        }
+      } else
 #pragma unroll 1
       for (int cb = 0; cb < N; cb += 32) {
         uint32_t v[32];
@@ -1216,7 +1251,7 @@ const bool g_umma_tma = [] { const char* e = std::getenv("P2M_UMMA_TMA"); return
 inline int epi_stage_bytes(int N) { return 4 * 32 * (N == 256 ? 16 : 32) * 4; }  // per-warp transpose staging
 size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g, int mode = 0) {
   const size_t fixed = 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + 8 * (2 * NS + 2 * XS + 8) + 16 +
-                       2 * (size_t)N * 4 + 16 + 128 + (size_t)epi_stage_bytes(N);
+                       2 * (size_t)N * 4 + 16 + 128 + (size_t)epi_stage_bytes(N) + (N == 64 ? 64 * 12 * 4 : 0);
   if (mode == 1)
     return fixed + (size_t)XS * TILE_M * FC * 4 + (size_t)XS * g.max_h1 * FC * 4 + 2 * (size_t)g.meta1_stride;
   if (mode == 2) return fixed + (size_t)XS * TILE_M * FC * 4 + 2 * (size_t)g.meta1_stride;
@@ -1288,6 +1323,8 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.y_col0 = a.y_col0;
   p.status = status;
   p.trace = g_umma_trace;
+  p.head_wt = (N == 64) ? a.head_wt : nullptr;
+  p.head_z = (N == 64) ? a.head_z : nullptr;
   p.tma = 0;
   std::memset(&p.tm_x, 0, sizeof(p.tm_x));
   std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
@@ -1608,6 +1645,10 @@ int launch_umma_pack_weights(const float* W, int fin, int fout, void* wpack, cud
 int launch_umma_conv(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   if (!umma_conv_supported(*a.g, a.fin, a.fout)) {
     set_error("umma_conv: unsupported shape");
+    return P2M_ERR_INVALID;
+  }
+  if (a.head_z != nullptr && (a.fout != 64 || a.head_wt == nullptr || a.ep.res != nullptr || a.plain)) {
+    set_error("umma_conv: the fused head needs fout == 64, no residual, conv mode");
     return P2M_ERR_INVALID;
   }
   switch (a.fout) {

@@ -477,6 +477,20 @@ __global__ void __launch_bounds__(256) k_thin_out(const int* __restrict__ rowptr
   for (int n = 0; n < fout; ++n) y[ro * fout + n] = apply_epilogue(o[n], r, n, ep);
 }
 
+int launch_thin_prep(const float* W, int fin, int fout, float* wt, cudaStream_t s) {
+  k_thin_prep<<<cdiv(fin * 12, 128), 128, 0, s>>>(W, fin, fout, wt);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+int launch_thin_tail(const DevLevel& g, int rows, int fout, const float* Z, float* U, const Epilogue& e, float* y,
+                     cudaStream_t s) {
+  k_thin_u<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, Z, U);
+  P2M_LAUNCH_OK();
+  k_thin_out<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, fout, Z, U, to_dev(e), y);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
 bool thin_conv_supported(int fin, int fout) { return fout <= 4 && (fin == 64 || fin == 32); }
 size_t thin_conv_scratch_floats(long long rows, int fin) { return (size_t)rows * 16 + (size_t)fin * 12; }
 

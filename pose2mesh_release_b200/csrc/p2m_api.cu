@@ -51,6 +51,7 @@ struct p2m_model {
   int* out_map = nullptr;        // optional fused output gather (vertex -> slot, -1 = dropped)
   int out_rows = 0;
   float* zero_row = nullptr;     // 128 B of zeros (halo source for the empty slots of ragged tiles)
+  int fuse_head = 1;             // eval: the 128 -> 64 conv's epilogue feeds the 64 -> 3 head directly (no 64-wide tensor)
   int split_t1 = 1;              // tcgen05 conv: T1 = L~x in a separate pass (k_cheb_t1) instead of on-chip halo recompute
   int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
   std::vector<cudaEvent_t> ev_beg, ev_end;
@@ -232,14 +233,20 @@ BwdMap map_scratch(const p2m_model* m, int B, void* base) {
 
 // ---- one conv layer, linear part + epilogue -------------------------------------------------
 // y = epilogue( [T0|T1|T2](x) * Wp^T )
+bool conv_on_tensor_cores(const p2m_model* m, const Layer& L, const unsigned char* wpack) {
+  return m->precision == P2M_PREC_FP16X3_TC && wpack != nullptr && umma_conv_supported(m->levels[L.level], L.fin, L.fout);
+}
 int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpool, const float* w_ref, float* T,
-                float* wp, unsigned char* wpack, const Epilogue& ep, float* y, cudaStream_t s) {
+                float* wp, unsigned char* wpack, const Epilogue& ep, float* y, cudaStream_t s,
+                const float* head_wt = nullptr, float* head_z = nullptr) {
   const int rows = B * L.V;
   const DevLevel& g = m->levels[L.level];
   P2M_TRY(launch_permute_w(w_ref, wp, L.fout, L.fin, s));  // k-major copy, also what backward's dT GEMM reads
-  if (m->precision == P2M_PREC_FP16X3_TC && wpack != nullptr && umma_conv_supported(g, L.fin, L.fout)) {
+  if (conv_on_tensor_cores(m, L, wpack)) {
     P2M_TRY(launch_umma_pack_weights(w_ref, L.fin, L.fout, wpack, s));
     UmmaConvArgs a;
+    a.head_wt = head_wt;
+    a.head_z = head_z;
     if (m->split_t1 && T != nullptr) {  // first sparse product as its own pass (T doubles as the T1 buffer)
       P2M_TRY(launch_cheb_t1(g, x, in_unpool, B, L.fin, T, s));
       a.t1 = T;
@@ -254,6 +261,10 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
     a.ep = ep;
     a.y = y;
     return launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s);
+  }
+  if (head_z != nullptr) {
+    set_error("conv_linear: fused head requested off the tensor-core path");
+    return P2M_ERR_INVALID;
   }
   if (thin_conv_supported(L.fin, L.fout) && ep.res == nullptr &&
       thin_conv_scratch_floats(rows, L.fin) <= (size_t)rows * 3 * L.fin) {
@@ -478,6 +489,11 @@ int p2m_debug_set_split_t1(p2m_model_t* m, int enable) {
   m->split_t1 = enable ? 1 : 0;
   return P2M_OK;
 }
+int p2m_debug_set_fuse_head(p2m_model_t* m, int enable) {
+  if (!m) return P2M_ERR_INVALID;
+  m->fuse_head = enable ? 1 : 0;
+  return P2M_OK;
+}
 
 int p2m_model_set_profiling(p2m_model_t* m, int enable) {
   if (!m) {
@@ -552,6 +568,7 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
   const float* cur = x;
   int cur_unpool = 0;
   int cur_buf = -1;  // rotating buffer id holding `cur` (eval)
+  float* head_z = nullptr;  // eval: Z of the thin head, produced by the previous layer's epilogue (see below)
   for (int b = 0; b < nb; ++b) {
     const Block& blk = m->blocks[b];
     const float* block_in = cur;
@@ -606,7 +623,27 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
           out = w.rot[out_buf];
         }
         if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_beg[li], s));
-        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s));
+        // Fused head: when the next layer is the network's thin head (64 -> 3, same block, no residual) and this
+        // layer runs on the tensor cores, its epilogue writes Z = act(y) W' (12 floats per row) instead of y, and
+        // the head shrinks to its two 4-wide sparse products: the 64-wide activation never reaches HBM.
+        bool fuse_head = false;
+        if (m->fuse_head && !last && li + 1 == nl - 1 && j + 1 < blk.n_layers && !with_res && !blk.has_residual &&
+            L.fout == 64 && rows >= 64 && conv_on_tensor_cores(m, L, w.wpack)) {
+          const Layer& H = m->layers[li + 1];
+          fuse_head = thin_conv_supported(H.fin, H.fout) && H.fin == L.fout && H.V == L.V;
+        }
+        if (head_z != nullptr) {  // this IS the head, its Z is already there
+          P2M_TRY(launch_thin_tail(m->levels[L.level], rows, L.fout, head_z, head_z + (size_t)rows * 12, ep, out, s));
+          head_z = nullptr;
+        } else if (fuse_head) {
+          float* Z = out;  // [rows][12] | U [rows][4] | W' [64][12] inside this layer's (unused) output buffer
+          float* wt = Z + (size_t)rows * 16;
+          P2M_TRY(launch_thin_prep(P->cl_w[li + 1], L.fout, m->layers[li + 1].fout, wt, s));
+          P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, wt, Z));
+          head_z = Z;
+        } else {
+          P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s));
+        }
         if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_end[li], s));
         cur = out;
         cur_buf = out_buf;

@@ -145,6 +145,11 @@ bool thin_conv_supported(int fin, int fout);
 size_t thin_conv_scratch_floats(long long rows, int fin);
 int launch_thin_conv(const DevLevel& g, const float* x, int in_unpool, int rows, int fin, int fout, const float* W,
                      const Epilogue& e, float* scratch, float* y, cudaStream_t s);
+// The same head in two pieces, for the fused eval path: the 128 -> 64 conv's epilogue produces Z = Y W' itself
+// (head_wt / head_z of UmmaConvArgs), the tail applies the two sparse products on the 4-wide rows.
+int launch_thin_prep(const float* W, int fin, int fout, float* wt, cudaStream_t s);
+int launch_thin_tail(const DevLevel& g, int rows, int fout, const float* Z, float* U, const Epilogue& e, float* y,
+                     cudaStream_t s);
 
 int launch_permute_w(const float* W, float* Wp, int fout, int fin, cudaStream_t s);      // [n,f*3+k] -> [n,k*fin+f]
 int launch_unpermute_w(const float* Wp, float* W, int fout, int fin, cudaStream_t s);    // inverse
@@ -190,6 +195,10 @@ struct UmmaConvArgs {
   const float* a_scale = nullptr;   // device scalar from launch_absmax_scale (or null)
   long long ldy = 0;                // 0: fout
   int y_col0 = 0;
+  // optional fused thin head (fout == 64 only): instead of storing y, the epilogue writes Z[row][12] = y_row * head_wt
+  // (head_wt = k_thin_prep's [64][12] table); y is then not written at all
+  const float* head_wt = nullptr;
+  float* head_z = nullptr;
 };
 // Host: build the per-tile halo metadata of one level (uploads; device pointers appended to `owned`).
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,

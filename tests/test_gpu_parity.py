@@ -244,6 +244,31 @@ def test_full_size_smpl_eval_against_oracle(precision):
     assert per_mesh_rel_err(y[pick][:, real], yo[:, real]) < TOL_Y   # the 6890 real vertices (base.py:130)
 
 
+@pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
+def test_fused_head_and_two_pass_match_the_separate_kernels(name):
+    """Ablations of the tensor-core path agree with each other (same fp32 math, different association):
+    fused 64->3 head on/off, separate T1 pass on/off; and the fused head also feeds the gathered output."""
+    n, seed, levels, mano = CASES[name]
+    model, mats, _ = make_model(name, "fp16x3")
+    model.eval()
+    x = torch.randn(5, 21 if mano else 17, 5, device=dev())
+    hier, d = model._hier, torch.cuda.current_device()
+    outs = {}
+    try:
+        for split_t1 in (True, False):
+            for fuse in (True, False):
+                hier.set_debug(d, split_t1=split_t1, fuse_head=fuse)
+                with torch.no_grad():
+                    outs[(split_t1, fuse)] = model(x).clone()
+        hier.set_debug(d, split_t1=True, fuse_head=True)
+        ref = outs[(False, False)]
+        for k, y in outs.items():
+            assert per_mesh_rel_err(y, ref) < 2e-5, k
+        assert hier.kernel_status(d) == 0
+    finally:
+        hier.set_debug(d, split_t1=True, fuse_head=True)
+
+
 def test_forward_host_matches_device_path():
     model, mats, mano = make_model("mano_like", "fp32")
     model.eval()
