@@ -757,26 +757,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         producer_barrier();
         if (tid == 0) trace_ev(p, 0, ptn, 5);
       }
-      // (2) T2 = 2 L~ T1 - X on the two tile rows this thread finishes
-      float4 tv[3][2];
-      {
-        const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
-        const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
-        tv[0][0] = lds_f4(xs_q + (row0 >> xsh) * 128);
-        tv[0][1] = lds_f4(xs_q + (row1 >> xsh) * 128);
-        tv[1][0] = lds_f4(t1s_q + row0 * 128);
-        tv[1][1] = lds_f4(t1s_q + row1 * 128);
-        const float4 a = tv[0][0], c2 = tv[0][1];
-        tv[2][0] = make_float4(2.f * g0.x - a.x, 2.f * g0.y - a.y, 2.f * g0.z - a.z, 2.f * g0.w - a.w);
-        tv[2][1] = make_float4(2.f * g1.x - c2.x, 2.f * g1.y - c2.y, 2.f * g1.z - c2.z, 2.f * g1.w - c2.w);
-      }
-      if (tid == 0) trace_ev(p, 0, ptn, 6);
-      // (3) split to fp16 (hi, lo) and write the three K-blocks; ONE generic->async proxy fence for all of
-      //     them (the fence drains the thread's outstanding shared stores and is expensive).  Odd row groups
-      //     store lo first: a warp then covers both 64-byte halves of its rows per store (conflict-free).
+      // (2) split to fp16 (hi, lo) and write the three K-blocks of the two tile rows this thread finishes.  The X and
+      //     T1 blocks go first: they need no gather, so the tensor core starts on them while (3) the second sparse
+      //     product T2 = 2 L~ T1 - X is still being gathered (with a 2-deep ring, N = 256, the T2 block re-uses the X
+      //     block's slot and would otherwise wait for its MMAs).  NS >= 3: ONE generic->async proxy fence for all
+      //     three blocks (the fence drains the thread's outstanding shared stores and is expensive); NS < 3: one per
+      //     block.  Odd row groups store lo first: a warp then covers both 64-byte halves of its rows per store.
       const uint32_t u0 = ucnt;
-#pragma unroll
-      for (int k = 0; k < 3; ++k, ++ucnt) {
+      auto emit = [&](const float4& v0, const float4& v1) {
         const int s = ucnt % NS;
         mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
         const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
@@ -784,7 +772,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         for (int ps = 0; ps < 2; ++ps) {
           const uint32_t i = ps ? row1 : row0;
           uint2 hi, lo;
-          split4(tv[k][ps], hi, lo);
+          split4(ps ? v1 : v0, hi, lo);
           const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
           if (rg & 1) {
             sts_u2(a_lo, lo);
@@ -794,11 +782,37 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
             sts_u2(a_lo, lo);
           }
         }
-        if (NS < 3) {  // ring shorter than a chunk: the third block re-uses the first block's slot -> publish each
+        if (NS < 3) {
           fence_async_proxy();
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
         }
+        ++ucnt;
+      };
+      if (NS < 3) {
+        const float4 x0 = lds_f4(xs_q + (row0 >> xsh) * 128), x1 = lds_f4(xs_q + (row1 >> xsh) * 128);
+        emit(x0, x1);
+        {
+          const float4 t10 = lds_f4(t1s_q + row0 * 128), t11 = lds_f4(t1s_q + row1 * 128);
+          emit(t10, t11);
+        }
+        const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
+        const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
+        if (tid == 0) trace_ev(p, 0, ptn, 6);
+        emit(make_float4(2.f * g0.x - x0.x, 2.f * g0.y - x0.y, 2.f * g0.z - x0.z, 2.f * g0.w - x0.w),
+             make_float4(2.f * g1.x - x1.x, 2.f * g1.y - x1.y, 2.f * g1.z - x1.z, 2.f * g1.w - x1.w));
+      } else {
+        // deep ring: gather first, then the three blocks back to back (measured faster than the early X/T1 emit:
+        // the gather then overlaps the previous chunk's tail instead of this chunk's own stores)
+        const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
+        const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
+        const float4 x0 = lds_f4(xs_q + (row0 >> xsh) * 128), x1 = lds_f4(xs_q + (row1 >> xsh) * 128);
+        const float4 t10 = lds_f4(t1s_q + row0 * 128), t11 = lds_f4(t1s_q + row1 * 128);
+        if (tid == 0) trace_ev(p, 0, ptn, 6);
+        emit(x0, x1);
+        emit(t10, t11);
+        emit(make_float4(2.f * g0.x - x0.x, 2.f * g0.y - x0.y, 2.f * g0.z - x0.z, 2.f * g0.w - x0.w),
+             make_float4(2.f * g1.x - x1.x, 2.f * g1.y - x1.y, 2.f * g1.z - x1.z, 2.f * g1.w - x1.w));
       }
       if (NS >= 3) {
         fence_async_proxy();
