@@ -238,10 +238,11 @@ bool conv_on_tensor_cores(const p2m_model* m, const Layer& L, const unsigned cha
 }
 int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpool, const float* w_ref, float* T,
                 float* wp, unsigned char* wpack, const Epilogue& ep, float* y, cudaStream_t s,
-                const float* head_wt = nullptr, float* head_z = nullptr) {
+                const float* head_wt = nullptr, float* head_z = nullptr, bool keep_wp = true) {
   const int rows = B * L.V;
   const DevLevel& g = m->levels[L.level];
-  P2M_TRY(launch_permute_w(w_ref, wp, L.fout, L.fin, s));  // k-major copy, also what backward's dT GEMM reads
+  // k-major copy of the weights: what the SIMT GEMM reads, and (training, keep_wp) what backward's SIMT dT GEMM reads
+  if (keep_wp || !conv_on_tensor_cores(m, L, wpack)) P2M_TRY(launch_permute_w(w_ref, wp, L.fout, L.fin, s));
   if (conv_on_tensor_cores(m, L, wpack)) {
     P2M_TRY(launch_umma_pack_weights(w_ref, L.fin, L.fout, wpack, s));
     UmmaConvArgs a;
@@ -639,10 +640,12 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
           float* Z = out;  // [rows][12] | U [rows][4] | W' [64][12] inside this layer's (unused) output buffer
           float* wt = Z + (size_t)rows * 16;
           P2M_TRY(launch_thin_prep(P->cl_w[li + 1], L.fout, m->layers[li + 1].fout, wt, s));
-          P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, wt, Z));
+          P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, wt, Z,
+                              false));
           head_z = Z;
         } else {
-          P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s));
+          P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, nullptr,
+                              nullptr, false));
         }
         if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_end[li], s));
         cur = out;
