@@ -1,26 +1,28 @@
 // tcgen05 (5th-gen tensor core) kernels of the MeshNet hot path for sm_100a.
 //
-// k_cheb_conv_umma — ONE kernel per Chebyshev graph-conv layer:
+// A Chebyshev graph-conv layer  Y = epilogue( [T0 | T1 | T2](X) * W^T ),  T1 = L~ X, T2 = 2 L~ T1 - X  is two launches:
 //
-//   Y[tile] = epilogue( [T0 | T1 | T2](X)[tile] * W^T ),   T1 = L~ X, T2 = 2 L~ T1 - X
-//
-// One persistent CTA per SM; a tile is 128 consecutive vertices of one mesh (a compact patch: the
-// reference's binary-tree vertex order makes rows [128p,128p+128) the descendants of one coarse node).
-//   * 16 producer warps build the A operand on chip, 32 features at a time: out of the staged 2-hop halo of
-//     X they run the two sparse products from shared memory with a tile-local CSR, split every fp32 value
-//     into an fp16 (hi, lo) pair and write it straight into the 128B-swizzled K-major UMMA layout.
-//     T0/T1/T2 are never materialised in HBM.
-//   * 2 loader warps stage the halo rows with 16-byte cp.async copies one chunk ahead (completion through
-//     cp.async.mbarrier.arrive.noinc) and prefetch the next tile's metadata blob with cp.async.bulk.
-//   * 1 thread streams the pre-packed fp16 (hi|lo) weight blocks with cp.async.bulk (TMA engine,
-//     mbarrier complete_tx).
+// k_cheb_t1        — T1 = L~ X for every row, written once to HBM (fp32): a 4-deep cp.async ring per 128-row tile,
+//                    gathers out of shared memory.
+// k_cheb_conv_umma — one persistent CTA per SM; a tile is 128 consecutive vertices of one mesh (a compact patch: the
+//                    reference's binary-tree vertex order makes rows [128p,128p+128) the descendants of one coarse node).
+//   * 16 producer warps build the A operand on chip, 32 features at a time.  They stage the tile's own X and T1
+//     rows (one 2-D TMA box each) and the T1 rows of the 1-hop halo (16-byte cp.async, completion through
+//     cp.async.mbarrier.arrive.noinc) one chunk ahead, run the second sparse product from shared memory with a
+//     tile-local CSR, split every fp32 value into an fp16 (hi, lo) pair and write it straight into the
+//     128B-swizzled K-major UMMA layout.  T2 is never materialised in HBM.  (Without a T1 buffer — p.t1 == nullptr —
+//     the same kernel stages the 2-hop halo of X and runs both sparse products on chip: the fully fused variant.)
+//   * 1 thread prefetches the next tile's metadata blob, 1 thread streams the pre-packed fp16 (hi|lo) weight
+//     blocks, both with cp.async.bulk (TMA engine, mbarrier complete_tx).
 //   * 1 thread issues tcgen05.mma (kind::f16, M=128, N=Fout, K=16) into a double-buffered TMEM accumulator:
 //     per 16 features three MMAs — hi*Whi + lo*Whi + hi*Wlo — an error-compensated product with ~2^-21
 //     relative error, which is what keeps the 1e-4 fp32 parity bar (plain TF32/FP16 does not, SURVEY.md §7
 //     "hard parts" 1).
-//   * 4 epilogue warps drain TMEM (tcgen05.ld) through the fused epilogue — bias / folded BatchNorm, ReLU,
-//     channel-resampled residual — while the next tile's main loop runs.
-// The unpool between levels is virtual: with in_unpool the halo rows are read from row r>>1 of the coarser
+//   * 4 epilogue warps drain TMEM (tcgen05.ld), transpose the accumulator rows through a swizzled per-warp staging
+//     buffer so that global accesses are coalesced, and apply the fused epilogue — bias / folded BatchNorm, ReLU,
+//     channel-resampled residual (or, for the network's last block, the 64 -> 3 head's projection) — while the
+//     next tile's main loop runs.
+// The unpool between levels is virtual: with in_unpool the rows are read from row r>>1 of the coarser
 // tensor.  Weights are pre-scaled by 2^6 so that their lo parts stay normal fp16 numbers (undone exactly in the
 // epilogue).  The same kernel in `plain` mode is the backward dT GEMM; k_cheb_dw_umma (below) is the dW
 // reduction with MN-major operands.  Every mbarrier wait is time-bounded (a protocol bug sets a status word
@@ -327,8 +329,8 @@ __device__ __forceinline__ void trace_ev(const KParams& p, int role, int& n, int
 
 // Warp roles (24 warps, one persistent CTA per SM):
 //   0..15  producers: SpMM out of shared memory + fp16 (hi,lo) split + swizzled A-block stores
-//   16,17  halo loaders: per (tile, chunk) stage the 2-hop halo rows of X with 16-byte cp.async copies
-//          (completion: cp.async.mbarrier.arrive.noinc); thread 0 also fetches the tile metadata (cp.async.bulk)
+//   16     thread 0 fetches the next tile's metadata (cp.async.bulk); warp 17 is idle (the rows are staged by the
+//          producers since the first sparse product moved out of this kernel)
 //   18     weight-block loader (one thread, cp.async.bulk)
 //   19     MMA issuer (one thread) and TMEM owner
 //   20..23 epilogue: TMEM -> registers -> fused epilogue -> HBM, overlapped with the next tile's main loop
@@ -563,49 +565,49 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           constexpr int IB = 4;  // row groups per batch (bounds the registers held by the residual pieces)
 #pragma unroll
           for (int i0 = 0; i0 < 32 / RPI; i0 += IB) {
-          float4 rv[IB];
-          if (p.ep.res != nullptr && p.res_identity) {
+            float4 rv[IB];
+            if (p.ep.res != nullptr && p.res_identity) {
+#pragma unroll
+              for (int i = 0; i < IB; ++i) {
+                const int rr = (i0 + i) * RPI + prow;
+                const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+                const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
+                const long long r = row0g + rr;
+                rv[i] = (rr < n_valid)
+                            ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + n))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < IB; ++i) {
               const int rr = (i0 + i) * RPI + prow;
               const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
               const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
-              const long long r = row0g + rr;
-              rv[i] = (rr < n_valid)
-                          ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + n))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
+              const float4 a = lds_f4(stg + rr * (EC * 4) + (pc << 4));
+              if (rr < n_valid) {
+                const float4 mu = *reinterpret_cast<const float4*>(ep_mul + n);
+                const float4 ad = *reinterpret_cast<const float4*>(ep_add + n);
+                float o[4] = {fmaf(a.x, mu.x, ad.x), fmaf(a.y, mu.y, ad.y), fmaf(a.z, mu.z, ad.z), fmaf(a.w, mu.w, ad.w)};
+                if (p.ep.relu) {
 #pragma unroll
-          for (int i = 0; i < IB; ++i) {
-            const int rr = (i0 + i) * RPI + prow;
-            const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
-            const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
-            const float4 a = lds_f4(stg + rr * (EC * 4) + (pc << 4));
-            if (rr < n_valid) {
-              const float4 mu = *reinterpret_cast<const float4*>(ep_mul + n);
-              const float4 ad = *reinterpret_cast<const float4*>(ep_add + n);
-              float o[4] = {fmaf(a.x, mu.x, ad.x), fmaf(a.y, mu.y, ad.y), fmaf(a.z, mu.z, ad.z), fmaf(a.w, mu.w, ad.w)};
-              if (p.ep.relu) {
+                  for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
+                const long long r = row0g + rr;
+                if (p.ep.res != nullptr) {
+                  if (p.res_identity) {
+                    o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
+                  } else {
+                    const float* res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-              }
-              const long long r = row0g + rr;
-              if (p.ep.res != nullptr) {
-                if (p.res_identity) {
-                  o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
-                } else {
-                  const float* res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float l = __ldg(p.ep.lam + n + e);
-                    o[e] += (1.f - l) * __ldg(res_row + __ldg(p.ep.i0 + n + e)) + l * __ldg(res_row + __ldg(p.ep.i1 + n + e));
+                    for (int e = 0; e < 4; ++e) {
+                      const float l = __ldg(p.ep.lam + n + e);
+                      o[e] += (1.f - l) * __ldg(res_row + __ldg(p.ep.i0 + n + e)) + l * __ldg(res_row + __ldg(p.ep.i1 + n + e));
+                    }
                   }
                 }
+                *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + n) = make_float4(o[0], o[1], o[2], o[3]);
               }
-              *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + n) = make_float4(o[0], o[1], o[2], o[3]);
             }
-          }
           }
           __syncwarp();
         }
