@@ -116,3 +116,43 @@ def test_meshnet_oracle_matches_reference(name):
             assert abs(got[2] - ref[2]) <= 2e-3 * ref[2] + 1e-12, k     # sum g^2
         if "running" in k:
             np.testing.assert_allclose(v.numpy(), z["after/" + k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["smpl_small", "smpl_like"])
+def test_padding_vertices_are_isolated_and_reduce_to_a_dense_map(name):
+    """Structure the next kernel round builds on: the fake vertices that the binary-tree
+    reorder pads each level with (lib/coarsening.py:214-258) are isolated in L~ and all carry the same diagonal
+    value c = 2/lmax - 1 (laplacian(): row = 1 on the diagonal, rescale_L: L/(lmax/2) - I), so on those rows the
+    Chebyshev conv is the dense map y = x (W0 + c W1 + (2c^2 - 1) W2)^T + b; and no real row ever reads a fake one."""
+    n, seed, levels, mano = CASES[name]
+    if name == "smpl_like":  # the fixture of the full-size case only stores digests: rebuild it with the oracle
+        j, sk, fp = _joint(mano)
+        _, mats, _, _ = go.build_coarse_graphs(go.synthetic_sphere_faces(n, seed), j, sk, fp, levels=levels)
+    else:
+        mats, _ = graph_from_fixture(name)
+    frac = []
+    for L in mats[: min(3, len(mats) - 1)]:
+        c = L.tocsr().astype(np.float64)
+        off = c.copy()
+        off.setdiag(0)
+        off.eliminate_zeros()
+        iso = np.diff(off.indptr) == 0
+        frac.append(iso.mean())
+        diag = c.diagonal()
+        assert iso.any() and np.ptp(diag[iso]) < 1e-12
+        # no edge from a connected row into an isolated one (the matrix is symmetric, so also none out of it)
+        assert not iso[off.indices].any()
+        cval = float(diag[iso][0])
+        g = torch.Generator().manual_seed(3)
+        fin, fout = 8, 5
+        x = torch.randn(2, c.shape[0], fin, generator=g)
+        w = torch.randn(fout, fin * 3, generator=g) * 0.2
+        b = torch.randn(fout, generator=g)
+        lap = mo.laplacians_to_torch([L], drop_second_coarsest=False)[0]
+        y = mo.cheb_conv(x, lap, w, b)
+        w3 = w.view(fout, fin, 3)
+        w_eff = w3[:, :, 0] + cval * w3[:, :, 1] + (2 * cval * cval - 1) * w3[:, :, 2]
+        y_iso = x[:, iso] @ w_eff.t() + b
+        assert rel_err(y[:, iso], y_iso) < 1e-5
+    if name == "smpl_like":
+        assert 0.40 < frac[0] < 0.48  # 5398 of 12288 rows at the finest SMPL-size level (SURVEY.md §8 a7)
