@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=24, help="meshes in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
+    ap.add_argument("--elide-padding", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="ablation: p2m_debug_set_elide_padding level (-1 = library default)")
     ap.add_argument("--mesh", default="smpl", choices=["smpl", "mano"],
                     help="smpl: 6890-vertex SMPL-size hierarchy (default, BASELINE configs[1,2,4]); "
                          "mano: 778-vertex MANO-size hierarchy 1088..68, 21 joints (configs[3], use --batch 1024)")
@@ -265,6 +267,8 @@ def main():
     model = Pose2Mesh(5, 3, graph_L, joint_set="mano" if args.mesh == "mano" else "human36")
     model.load_state_dict(randomize_bn_({k: v.clone() for k, v in model.state_dict().items()}))
     model = model.to(dev).set_precision(args.precision)
+    if args.elide_padding >= 0:
+        model._hier.set_debug(local, elide_padding=args.elide_padding)
     B = args.batch
     g = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.randn(B, n_joint, 5, generator=g).pin_memory()

@@ -94,6 +94,11 @@ int p2m_debug_set_split_t1(p2m_model_t* m, int enable);
 /* Debug / ablation: 1 (default) = in eval mode the 128->64 conv's epilogue produces the 64->3 head's projections
  * itself (the 64-wide activation is never written); 0 = the two layers run separately.                         */
 int p2m_debug_set_fuse_head(p2m_model_t* m, int enable);
+/* Padding-vertex elision: the isolated padding vertices of each level (the fake nodes of the reference's binary-tree
+ * reorder, lib/coarsening.py:214-258) go through a plain GEMM with the combined weights W0 + c W1 + (2c^2-1) W2, the
+ * connected rows through the conv on index-list tiles.  Same results up to fp32 association.  1 (default) = on levels
+ * where at least 40 % of the rows are isolated, 2 = wherever the tile families exist, 0 = off.                       */
+int p2m_debug_set_elide_padding(p2m_model_t* m, int enable);
 
 /* Bytes of device workspace p2m_meshnet_forward needs for batch B.  In training mode the workspace
  * also carries what p2m_meshnet_backward reads, so it must stay alive and untouched in between.   */

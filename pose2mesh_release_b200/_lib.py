@@ -72,7 +72,7 @@ class ConvBwdArgs(C.Structure):
 
 EXPORTS = [
     "p2m_model_create", "p2m_model_destroy", "p2m_model_num_layers", "p2m_model_layer_info",
-    "p2m_model_set_precision", "p2m_debug_kernel_status", "p2m_debug_set_trace", "p2m_debug_set_split_t1", "p2m_debug_set_fuse_head", "p2m_model_set_profiling", "p2m_model_layer_times_ms", "p2m_meshnet_workspace_bytes", "p2m_meshnet_backward_scratch_bytes",
+    "p2m_model_set_precision", "p2m_debug_kernel_status", "p2m_debug_set_trace", "p2m_debug_set_split_t1", "p2m_debug_set_fuse_head", "p2m_debug_set_elide_padding", "p2m_model_set_profiling", "p2m_model_layer_times_ms", "p2m_meshnet_workspace_bytes", "p2m_meshnet_backward_scratch_bytes",
     "p2m_meshnet_forward", "p2m_meshnet_backward", "p2m_model_set_output_gather", "p2m_meshnet_forward_vertices", "p2m_meshnet_host_io_bytes", "p2m_meshnet_forward_host",
     "p2m_cheb_conv_workspace_bytes", "p2m_cheb_conv_fwd", "p2m_cheb_conv_bwd", "p2m_graph_match_level",
     "p2m_last_error", "p2m_version", "p2m_launch_count", "p2m_launch_count_reset",
@@ -114,6 +114,8 @@ def load() -> C.CDLL:
         lib.p2m_debug_set_split_t1.restype = C.c_int
         lib.p2m_debug_set_fuse_head.argtypes = [vp, C.c_int]
         lib.p2m_debug_set_fuse_head.restype = C.c_int
+        lib.p2m_debug_set_elide_padding.argtypes = [vp, C.c_int]
+        lib.p2m_debug_set_elide_padding.restype = C.c_int
         lib.p2m_debug_set_trace.argtypes = [vp]
         lib.p2m_debug_set_trace.restype = C.c_int
         lib.p2m_debug_kernel_status.argtypes = [vp, c_int32_p]

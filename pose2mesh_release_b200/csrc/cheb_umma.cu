@@ -313,6 +313,8 @@ struct KParams {
   float* y;
   int* status;
   long long* trace;  // optional [8][512] event log of CTA 0 (debug): (event << 48) | clock
+  int own_table;         // 1: the tile's rows are the index list at the head of its metadata blob (TileSet), not
+                         //    the consecutive rows [128 pat, 128 pat + 128)
   const float* head_wt;  // optional fused thin head (N == 64): epilogue writes head_z[row][12] = y_row * head_wt[64][12]
   float* head_z;
   int tma;           // 1: the tile's own rows of x (and t1) arrive by one 2-D TMA load each (T1-given / plain mode on
@@ -372,7 +374,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
   constexpr int EC = (N == 256) ? 16 : 32;
   unsigned char* epi_stage =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ep_add + N) + 127) & ~(uintptr_t)127);
-  float* head_w_s = reinterpret_cast<float*>(epi_stage + 4 * 32 * EC * 4);  // [64][12] (N == 64 with a fused head)
+  int* own_s = reinterpret_cast<int*>(epi_stage + 4 * 32 * EC * 4);  // [4 warps][32] vertex id of each epilogue row
+  float* head_w_s = reinterpret_cast<float*>(own_s + 4 * 32);        // [64][12] (N == 64 with a fused head)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -500,16 +503,30 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.P, pat = tile - b * p.P;
       const int as = it & 1;
-      const int n_valid = min(TILE_M, p.V - pat * TILE_M) - lane_base;  // rows of this warp's 32 that exist
-      const long long row0g = (long long)b * p.V + (long long)pat * TILE_M + lane_base;
+      // vertex id of each of this warp's 32 accumulator rows (-1: the slot holds no vertex)
+      const long long mesh0 = (long long)b * p.V;
+      int* own_w = own_s + (warp - W_EPI0) * 32;
+      {
+        int v;
+        if (p.own_table) {
+          v = __ldg(reinterpret_cast<const int*>(p.meta + (size_t)pat * p.meta_stride + 64) + lane_base + lane);
+        } else {
+          v = pat * TILE_M + lane_base + lane;
+          if (v >= p.V) v = -1;
+        }
+        __syncwarp();  // the previous tile's readers of own_w are done
+        own_w[lane] = v;
+        __syncwarp();
+      }
       if (p.ep.res != nullptr) {
         // pull this tile's residual rows into L2 while its main loop is still running: the reads below then pay
         // an L2 hit instead of a DRAM round trip per batch
         const int lpr = (p.ep.res_F * 4 + 127) >> 7;  // 128-byte lines per residual row
         for (int j = lane; j < 32 * lpr; j += 32) {
           const int rr = j / lpr, ln = j - rr * lpr;
-          if (rr < n_valid) {
-            const long long r = row0g + rr;
+          const int vtx = own_w[rr];
+          if (vtx >= 0) {
+            const long long r = mesh0 + vtx;
             prefetch_l2(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + ln * 32);
           }
         }
@@ -540,8 +557,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
             z[8] = fmaf(t, w2.x, z[8]); z[9] = fmaf(t, w2.y, z[9]); z[10] = fmaf(t, w2.z, z[10]); z[11] = fmaf(t, w2.w, z[11]);
           }
         }
-        if (lane < n_valid) {
-          float4* zr = reinterpret_cast<float4*>(p.head_z + (row0g + lane) * 12);
+        if (own_w[lane] >= 0) {
+          float4* zr = reinterpret_cast<float4*>(p.head_z + (mesh0 + own_w[lane]) * 12);
           zr[0] = make_float4(z[0], z[1], z[2], z[3]);
           zr[1] = make_float4(z[4], z[5], z[6], z[7]);
           zr[2] = make_float4(z[8], z[9], z[10], z[11]);
@@ -572,8 +589,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
                 const int rr = (i0 + i) * RPI + prow;
                 const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
                 const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
-                const long long r = row0g + rr;
-                rv[i] = (rr < n_valid)
+                const int vtx = own_w[rr];
+                const long long r = mesh0 + vtx;
+                rv[i] = (vtx >= 0)
                             ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + n))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
               }
@@ -584,7 +602,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
               const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
               const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
               const float4 a = lds_f4(stg + rr * (EC * 4) + (pc << 4));
-              if (rr < n_valid) {
+              const int vtx = own_w[rr];
+              if (vtx >= 0) {
                 const float4 mu = *reinterpret_cast<const float4*>(ep_mul + n);
                 const float4 ad = *reinterpret_cast<const float4*>(ep_add + n);
                 float o[4] = {fmaf(a.x, mu.x, ad.x), fmaf(a.y, mu.y, ad.y), fmaf(a.z, mu.z, ad.z), fmaf(a.w, mu.w, ad.w)};
@@ -592,7 +611,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
 #pragma unroll
                   for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
                 }
-                const long long r = row0g + rr;
+                const long long r = mesh0 + vtx;
                 if (p.ep.res != nullptr) {
                   if (p.res_identity) {
                     o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
@@ -1265,13 +1284,22 @@ const bool g_umma_tma = [] { const char* e = std::getenv("P2M_UMMA_TMA"); return
 
 // mode: 0 = fused (X with its 2-hop halo staged, T1 recomputed on chip), 1 = T1 given, 2 = plain GEMM
 inline int epi_stage_bytes(int N) { return 4 * 32 * (N == 256 ? 16 : 32) * 4; }  // per-warp transpose staging
-size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g, int mode = 0) {
+size_t smem_bytes_dims(int N, int NS, int XS, int max_h1, int max_h2, int meta_stride, int mode) {
   const size_t fixed = 1024 + (size_t)NS * (A_BLOCK_BYTES + N * 128) + 8 * (2 * NS + 2 * XS + 8) + 16 +
-                       2 * (size_t)N * 4 + 16 + 128 + (size_t)epi_stage_bytes(N) + (N == 64 ? 64 * 12 * 4 : 0);
-  if (mode == 1)
-    return fixed + (size_t)XS * TILE_M * FC * 4 + (size_t)XS * g.max_h1 * FC * 4 + 2 * (size_t)g.meta1_stride;
-  if (mode == 2) return fixed + (size_t)XS * TILE_M * FC * 4 + 2 * (size_t)g.meta1_stride;
-  return fixed + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 + 2 * (size_t)g.meta_stride;
+                       2 * (size_t)N * 4 + 16 + 128 + (size_t)epi_stage_bytes(N) + 4 * 32 * 4 +
+                       (N == 64 ? 64 * 12 * 4 : 0);
+  if (mode == 1) return fixed + (size_t)XS * TILE_M * FC * 4 + (size_t)XS * max_h1 * FC * 4 + 2 * (size_t)meta_stride;
+  if (mode == 2) return fixed + (size_t)XS * TILE_M * FC * 4 + 2 * (size_t)meta_stride;
+  return fixed + (size_t)XS * max_h2 * FC * 4 + (size_t)max_h1 * FC * 4 + 2 * (size_t)meta_stride;
+}
+size_t smem_bytes_for(int N, int NS, int XS, const DevLevel& g, int mode = 0) {
+  return smem_bytes_dims(N, NS, XS, g.max_h1, g.max_h2, mode ? g.meta1_stride : g.meta_stride, mode);
+}
+// the same for an explicit launch: the level's consecutive tiles, or the tile family the caller selected
+size_t smem_bytes_args(int N, int NS, int XS, const UmmaConvArgs& a) {
+  const int mode = a.plain ? 2 : (a.t1 != nullptr ? 1 : 0);
+  if (a.tiles != nullptr) return smem_bytes_dims(N, NS, XS, a.tiles->max_h1, a.tiles->max_h1, a.tiles->stride, mode);
+  return smem_bytes_for(N, NS, XS, *a.g, mode);
 }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 inline int ring_stages(int N) { return N == 256 ? 2 : 3; }
@@ -1312,7 +1340,7 @@ template <int N, int NS, int XS>
 int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   const DevLevel& g = *a.g;
   const int mode = a.plain ? 2 : (a.t1 != nullptr ? 1 : 0);
-  const size_t smem = smem_bytes_for(N, NS, XS, g, mode);
+  const size_t smem = smem_bytes_args(N, NS, XS, a);
   auto kern = k_cheb_conv_umma<N, NS, XS>;
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KParams p;
@@ -1321,12 +1349,22 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.V = g.V;
   p.P = g.n_pattern;
   p.fin = a.fin;
-  p.n_tiles = a.batch * g.n_pattern;
   p.meta = mode ? g.tile_meta1 : g.tile_meta;
   p.meta_bytes = mode ? g.tile_meta1_bytes : g.tile_meta_bytes;
   p.meta_stride = mode ? g.meta1_stride : g.meta_stride;
   p.max_h1 = g.max_h1;
   p.max_h2 = g.max_h2;
+  p.own_table = 0;
+  if (a.tiles != nullptr) {  // index-list tiles (mode 1 / 2 only, checked by the caller)
+    p.P = a.tiles->n_pattern;
+    p.meta = a.tiles->meta;
+    p.meta_bytes = a.tiles->bytes;
+    p.meta_stride = a.tiles->stride;
+    p.max_h1 = a.tiles->max_h1;
+    p.max_h2 = a.tiles->max_h1;
+    p.own_table = 1;
+  }
+  p.n_tiles = a.batch * p.P;
   p.wpack = static_cast<const unsigned char*>(a.wpack);
   p.zero_row = zero_row;
   p.ep = to_dev(a.ep);
@@ -1344,7 +1382,7 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.tma = 0;
   std::memset(&p.tm_x, 0, sizeof(p.tm_x));
   std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
-  if ((a.t1 != nullptr || a.plain) && g.V % TILE_M == 0 && g_umma_tma) {
+  if ((a.t1 != nullptr || a.plain) && a.tiles == nullptr && g.V % TILE_M == 0 && g_umma_tma) {
     const long long rows = (long long)a.batch * g.V;
     bool ok = make_row_tmap(&p.tm_x, a.x, a.in_unpool ? rows / 2 : rows, a.fin, a.in_unpool ? TILE_M / 2 : TILE_M);
     if (ok && a.t1 != nullptr) ok = make_row_tmap(&p.tm_t1, a.t1, rows, a.fin, TILE_M);
@@ -1360,8 +1398,11 @@ template <int N>
 int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   constexpr int NS = (N == 256) ? 2 : 3;
   if (a.t1 != nullptr || a.plain) {
-    if (smem_bytes_for(N, NS, 2, *a.g, a.plain ? 2 : 1) <= SMEM_LIMIT)
-      return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
+    if (smem_bytes_args(N, NS, 2, a) <= SMEM_LIMIT) return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
+    if (smem_bytes_args(N, NS, 1, a) > SMEM_LIMIT) {
+      set_error("umma_conv: tile family does not fit shared memory");
+      return P2M_ERR_INVALID;
+    }
     return launch_cfg<N, NS, 1>(a, status, zero_row, sm_count, s);
   }
   if (x_stages(N, *a.g) == 2) return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
@@ -1373,6 +1414,111 @@ int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_c
 // =====================================================================================
 // host side
 // =====================================================================================
+namespace {
+// Trimmed blob of one tile whose 128 own rows are given by an index list (-1 = empty slot): own rows, their 1-hop
+// halo, the CSR of the own rows with staged-row slots as columns, the own rows in length-sorted order.
+bool make_indexed_blob(const std::vector<int>& own, const int* rowptr, const int* colidx, const float* val,
+                       std::vector<int>* slot_of, std::vector<unsigned char>* blob, int* h1_out) {
+  std::vector<int> halo(own);
+  int n_rows = 0;
+  for (int i = 0; i < TILE_M; ++i)
+    if (own[i] >= 0) {
+      (*slot_of)[own[i]] = i;
+      ++n_rows;
+    }
+  for (int i = 0; i < TILE_M; ++i) {
+    if (own[i] < 0) continue;
+    for (int e = rowptr[own[i]]; e < rowptr[own[i] + 1]; ++e) {
+      const int v = colidx[e];
+      if ((*slot_of)[v] < 0) {
+        (*slot_of)[v] = (int)halo.size();
+        halo.push_back(v);
+      }
+    }
+  }
+  const int h1 = (int)halo.size();
+  std::vector<unsigned short> rp(TILE_M + 1, 0);
+  std::vector<unsigned int> ent;
+  for (int i = 0; i < TILE_M; ++i) {
+    if (own[i] >= 0)
+      for (int e = rowptr[own[i]]; e < rowptr[own[i] + 1]; ++e) {
+        unsigned int bits;
+        std::memcpy(&bits, &val[e], 4);
+        ent.push_back((unsigned int)(*slot_of)[colidx[e]] * 128u);
+        ent.push_back(bits);
+      }
+    rp[i + 1] = (unsigned short)(ent.size() / 2);
+  }
+  for (int v : halo)
+    if (v >= 0) (*slot_of)[v] = -1;
+  const int nnz = (int)(ent.size() / 2);
+  if (h1 > 512 || nnz > 65535) return false;
+  std::vector<unsigned short> ord2(TILE_M);
+  for (int i = 0; i < TILE_M; ++i) ord2[i] = (unsigned short)i;
+  std::stable_sort(ord2.begin(), ord2.end(), [&](unsigned short a, unsigned short b2) {
+    return (int)rp[a + 1] - (int)rp[a] > (int)rp[b2 + 1] - (int)rp[b2];
+  });
+  TileHeader t{};
+  t.n_rows = n_rows;
+  t.h1 = h1;
+  t.h2 = h1;
+  t.nnz = nnz;
+  int o1 = 64;
+  t.off_halo = o1; o1 += up16(h1 * 4);
+  t.off_rp = o1;   o1 += up16((TILE_M + 1) * 2);
+  t.off_ent = o1;  o1 += up16(nnz * 8);
+  t.off_ord2 = o1; o1 += up16(TILE_M * 2);
+  t.off_ord1 = t.off_ord2;
+  t.bytes = o1;
+  blob->assign(o1, 0);
+  std::memcpy(blob->data(), &t, sizeof(t));
+  std::memcpy(blob->data() + t.off_halo, halo.data(), (size_t)h1 * 4);
+  std::memcpy(blob->data() + t.off_rp, rp.data(), (TILE_M + 1) * 2);
+  if (nnz) std::memcpy(blob->data() + t.off_ent, ent.data(), (size_t)nnz * 8);
+  std::memcpy(blob->data() + t.off_ord2, ord2.data(), TILE_M * 2);
+  *h1_out = h1;
+  return true;
+}
+
+// Tiles of 128 consecutive entries of `rows` (ascending vertex ids), uploaded as one TileSet.
+int build_tileset(const std::vector<int>& rows, const int* rowptr, const int* colidx, const float* val, int V,
+                  TileSet* ts, std::vector<void*>* owned) {
+  const int P = ((int)rows.size() + TILE_M - 1) / TILE_M;
+  std::vector<std::vector<unsigned char>> blobs(P);
+  std::vector<int> slot_of(V, -1);
+  int stride = 0, max_h1 = 0;
+  for (int pt = 0; pt < P; ++pt) {
+    std::vector<int> own(TILE_M, -1);
+    for (int i = 0; i < TILE_M && pt * TILE_M + i < (int)rows.size(); ++i) own[i] = rows[pt * TILE_M + i];
+    int h1 = 0;
+    if (!make_indexed_blob(own, rowptr, colidx, val, &slot_of, &blobs[pt], &h1)) return P2M_ERR_INVALID;
+    stride = std::max(stride, (int)blobs[pt].size());
+    max_h1 = std::max(max_h1, h1);
+  }
+  stride = (stride + 127) & ~127;
+  std::vector<unsigned char> all((size_t)P * stride, 0);
+  std::vector<int> bytes(P);
+  for (int pt = 0; pt < P; ++pt) {
+    std::memcpy(all.data() + (size_t)pt * stride, blobs[pt].data(), blobs[pt].size());
+    bytes[pt] = (int)blobs[pt].size();
+  }
+  unsigned char* d_meta = nullptr;
+  int* d_bytes = nullptr;
+  P2M_CUDA_OK(cudaMalloc(&d_meta, all.size()));
+  owned->push_back(d_meta);
+  P2M_CUDA_OK(cudaMalloc(&d_bytes, sizeof(int) * P));
+  owned->push_back(d_bytes);
+  P2M_CUDA_OK(cudaMemcpy(d_meta, all.data(), all.size(), cudaMemcpyHostToDevice));
+  P2M_CUDA_OK(cudaMemcpy(d_bytes, bytes.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+  ts->meta = d_meta;
+  ts->bytes = d_bytes;
+  ts->stride = stride;
+  ts->n_pattern = P;
+  ts->max_h1 = max_h1;
+  return P2M_OK;
+}
+}  // namespace
+
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
                           std::vector<void*>* owned) {
   const int P = (V + TILE_M - 1) / TILE_M;
@@ -1517,6 +1663,33 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
     out->tile_meta1_bytes = d_bytes1;
     out->meta1_stride = stride1;
   }
+  {
+    // padding-vertex elision: rows whose only entry is the diagonal, all with the same value
+    std::vector<int> real_rows, iso_rows;
+    float c = 0.f;
+    bool uniform = true;
+    for (int v = 0; v < V; ++v) {
+      const bool iso = (rowptr[v + 1] - rowptr[v] == 1) && colidx[rowptr[v]] == v;
+      if (iso) {
+        if (iso_rows.empty()) c = val[rowptr[v]];
+        if (val[rowptr[v]] != c) uniform = false;
+        iso_rows.push_back(v);
+      } else {
+        real_rows.push_back(v);
+      }
+    }
+    out->n_iso = 0;
+    if (uniform && (int)iso_rows.size() >= TILE_M && (int)real_rows.size() >= TILE_M) {
+      TileSet rt, it;
+      if (build_tileset(real_rows, rowptr, colidx, val, V, &rt, owned) == P2M_OK &&
+          build_tileset(iso_rows, rowptr, colidx, val, V, &it, owned) == P2M_OK && rt.max_h1 <= 256) {
+        out->real_tiles = rt;
+        out->iso_tiles = it;
+        out->n_iso = (int)iso_rows.size();
+        out->iso_diag = c;
+      }
+    }
+  }
   out->n_pattern = P;
   out->tile_meta = d_meta;
   out->tile_meta_bytes = d_bytes;
@@ -1582,16 +1755,20 @@ int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, 
   return P2M_OK;
 }
 
-int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s) {
+int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s,
+                   const TileSet* tiles) {
   if (g.tile_meta == nullptr || fin % FC != 0) {
     set_error("cheb_t1: unsupported shape");
     return P2M_ERR_INVALID;
   }
-  if (g.max_h1 > 256) {  // 4 staged slots per row group
+  const int max_h1 = tiles ? tiles->max_h1 : g.max_h1;
+  const int stride = tiles ? tiles->stride : g.meta1_stride;
+  const int n_pattern = tiles ? tiles->n_pattern : g.n_pattern;
+  if (max_h1 > 256) {  // 4 staged slots per row group
     set_error("cheb_t1: halo too large");
     return P2M_ERR_INVALID;
   }
-  auto smem_for = [&](int stages) { return (size_t)g.meta1_stride + stages * (size_t)g.max_h1 * FC * 4 + 16; };
+  auto smem_for = [&](int stages) { return (size_t)stride + stages * (size_t)max_h1 * FC * 4 + 16; };
   const size_t half_sm = (228 * 1024) / 2 - 1024;  // two CTAs per SM (1 KB per CTA is reserved by the system)
   const int stages = smem_for(4) <= half_sm ? 4 : (smem_for(3) <= half_sm ? 3 : 2);
   const size_t smem = smem_for(stages);
@@ -1601,14 +1778,14 @@ int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, 
   p.x = x;
   p.in_unpool = in_unpool;
   p.V = g.V;
-  p.P = g.n_pattern;
+  p.P = n_pattern;
   p.fin = fin;
-  p.meta = g.tile_meta1;
-  p.meta_bytes = g.tile_meta1_bytes;
-  p.meta_stride = g.meta1_stride;
-  p.max_h1 = g.max_h1;
+  p.meta = tiles ? tiles->meta : g.tile_meta1;
+  p.meta_bytes = tiles ? tiles->bytes : g.tile_meta1_bytes;
+  p.meta_stride = stride;
+  p.max_h1 = max_h1;
   p.t1 = t1;
-  kern<<<batch * g.n_pattern, 512, smem, s>>>(p);
+  kern<<<batch * n_pattern, 512, smem, s>>>(p);
   P2M_LAUNCH_OK();
   return P2M_OK;
 }
@@ -1640,6 +1817,34 @@ __global__ void __launch_bounds__(256) k_pack_plain(const float* __restrict__ Bm
   *reinterpret_cast<uint4*>(out + (size_t)c * N * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
 }
 
+// the same image for the combined weights of the isolated rows, straight from the reference layout
+__global__ void __launch_bounds__(256) k_pack_iso(const float* __restrict__ W, float c, int fin, int fout,
+                                                  unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int total = (fin / FC) * fout * 8;
+  if (idx >= total) return;
+  const int j = idx & 7;
+  const int n = (idx >> 3) % fout;
+  const int cc = (idx >> 3) / fout;
+  const int f0 = cc * FC + (j & 3) * 8;
+  const float c2 = 2.f * c * c - 1.f;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float* wr = W + (size_t)n * fin * 3 + (size_t)(f0 + e) * 3;
+    const float w = (wr[0] + c * wr[1] + c2 * wr[2]) * W_SCALE;
+    const __half hi = __float2half_rn(w);
+    h[e] = (j < 4) ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)cc * fout * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
+}
+int launch_umma_pack_iso(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s) {
+  const int total = (fin / FC) * fout * 8;
+  k_pack_iso<<<(total + 255) / 256, 256, 0, s>>>(W, c, fin, fout, static_cast<unsigned char*>(wpack));
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
 size_t umma_plain_pack_bytes(int N, int K) { return (size_t)(K / FC) * N * 128; }
 
 int launch_umma_pack_plain(const float* Bmat, long long ld_n, long long ld_k, int N, int K, void* wpack, cudaStream_t s) {
@@ -1663,8 +1868,12 @@ int launch_umma_conv(const UmmaConvArgs& a, int* status, const float* zero_row, 
     set_error("umma_conv: unsupported shape");
     return P2M_ERR_INVALID;
   }
-  if (a.head_z != nullptr && (a.fout != 64 || a.head_wt == nullptr || a.ep.res != nullptr || a.plain)) {
-    set_error("umma_conv: the fused head needs fout == 64, no residual, conv mode");
+  if (a.head_z != nullptr && (a.fout != 64 || a.head_wt == nullptr || a.ep.res != nullptr)) {
+    set_error("umma_conv: the fused head needs fout == 64 and no residual");
+    return P2M_ERR_INVALID;
+  }
+  if (a.tiles != nullptr && ((a.t1 == nullptr && !a.plain) || a.tiles->max_h1 > 256 || a.tiles->n_pattern <= 0)) {
+    set_error("umma_conv: index-list tiles need the T1-given or plain mode and at most 256 staged rows");
     return P2M_ERR_INVALID;
   }
   switch (a.fout) {

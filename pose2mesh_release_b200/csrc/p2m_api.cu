@@ -51,6 +51,9 @@ struct p2m_model {
   int* out_map = nullptr;        // optional fused output gather (vertex -> slot, -1 = dropped)
   int out_rows = 0;
   float* zero_row = nullptr;     // 128 B of zeros (halo source for the empty slots of ragged tiles)
+  int elide_padding = 1;         // tcgen05 conv: isolated padding vertices through a plain GEMM with combined weights;
+                                 // 1 = on levels where they are >= 40 % of the rows (measured break-even), 2 = wherever
+                                 // the tile families exist, 0 = off (p2m_debug_set_elide_padding)
   int fuse_head = 1;             // eval: the 128 -> 64 conv's epilogue feeds the 64 -> 3 head directly (no 64-wide tensor)
   int split_t1 = 1;              // tcgen05 conv: T1 = L~x in a separate pass (k_cheb_t1) instead of on-chip halo recompute
   int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
@@ -238,7 +241,7 @@ bool conv_on_tensor_cores(const p2m_model* m, const Layer& L, const unsigned cha
 }
 int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpool, const float* w_ref, float* T,
                 float* wp, unsigned char* wpack, const Epilogue& ep, float* y, cudaStream_t s,
-                const float* head_wt = nullptr, float* head_z = nullptr, bool keep_wp = true) {
+                const float* head_wt = nullptr, float* head_z = nullptr, bool keep_wp = true, bool may_elide = false) {
   const int rows = B * L.V;
   const DevLevel& g = m->levels[L.level];
   // k-major copy of the weights: what the SIMT GEMM reads, and (training, keep_wp) what backward's SIMT dT GEMM reads
@@ -248,8 +251,13 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
     UmmaConvArgs a;
     a.head_wt = head_wt;
     a.head_z = head_z;
+    // Padding-vertex elision (DevLevel::n_iso): connected rows through the conv on index-list tiles, isolated rows
+    // through a plain GEMM with the combined weights.  Needs the T buffer of the network schedules (3 Fin wide: the
+    // packed combined weights live behind the T1 part).
+    const bool elide = may_elide && m->elide_padding && m->split_t1 && T != nullptr && g.n_iso > 0 &&
+                       rows >= 2 * L.fout && (m->elide_padding >= 2 || 5LL * g.n_iso >= 2LL * g.V);
     if (m->split_t1 && T != nullptr) {  // first sparse product as its own pass (T doubles as the T1 buffer)
-      P2M_TRY(launch_cheb_t1(g, x, in_unpool, B, L.fin, T, s));
+      P2M_TRY(launch_cheb_t1(g, x, in_unpool, B, L.fin, T, s, elide ? &g.real_tiles : nullptr));
       a.t1 = T;
     }
     a.g = &g;
@@ -261,6 +269,15 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
     a.wpack = wpack;
     a.ep = ep;
     a.y = y;
+    if (!elide) return launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s);
+    a.tiles = &g.real_tiles;
+    P2M_TRY(launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s));
+    unsigned char* w_iso = reinterpret_cast<unsigned char*>(T + (size_t)rows * L.fin);
+    P2M_TRY(launch_umma_pack_iso(w_ref, g.iso_diag, L.fin, L.fout, w_iso, s));
+    a.t1 = nullptr;
+    a.plain = 1;
+    a.tiles = &g.iso_tiles;
+    a.wpack = w_iso;
     return launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s);
   }
   if (head_z != nullptr) {
@@ -490,6 +507,11 @@ int p2m_debug_set_split_t1(p2m_model_t* m, int enable) {
   m->split_t1 = enable ? 1 : 0;
   return P2M_OK;
 }
+int p2m_debug_set_elide_padding(p2m_model_t* m, int enable) {
+  if (!m) return P2M_ERR_INVALID;
+  m->elide_padding = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+  return P2M_OK;
+}
 int p2m_debug_set_fuse_head(p2m_model_t* m, int enable) {
   if (!m) return P2M_ERR_INVALID;
   m->fuse_head = enable ? 1 : 0;
@@ -641,11 +663,11 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
           float* wt = Z + (size_t)rows * 16;
           P2M_TRY(launch_thin_prep(P->cl_w[li + 1], L.fout, m->layers[li + 1].fout, wt, s));
           P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, wt, Z,
-                              false));
+                              false, true));
           head_z = Z;
         } else {
           P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, nullptr,
-                              nullptr, false));
+                              nullptr, false, true));
         }
         if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_end[li], s));
         cur = out;
@@ -655,7 +677,8 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
         Epilogue ep;
         ep.bias = P->cl_b[li];
         float* z = last ? y : w.z[li];
-        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp[li], w.wpack, ep, z, s));
+        P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp[li], w.wpack, ep, z, s, nullptr, nullptr,
+                            true, true));
         if (L.bn) {
           P2M_TRY(launch_col_stats(z, rows, L.fout, w.sums, s));
           P2M_TRY(launch_bn_finalize(w.sums, rows, L.fout, P->bn_w[li], P->bn_b[li], P->bn_rm[li], P->bn_rv[li],

@@ -44,6 +44,16 @@ void count_launch(int n = 1);
 // ---------------------------------------------------------------- device-resident hierarchy level
 // L~ of one level in CSR with RELATIVE column offsets: the neighbour of flat activation row
 // r = b*V + v is row r + reloff[p], so kernels never need (b, v) separately (block-diagonal I_B (x) L~).
+// A family of 128-row tile patterns of one level whose rows are given by index lists (trimmed blobs: the tile's own
+// rows, their 1-hop halo, the CSR of the own rows) instead of being the consecutive rows [128 p, 128 p + 128).
+struct TileSet {
+  const unsigned char* meta = nullptr;  // [n_pattern][stride]
+  const int* bytes = nullptr;           // [n_pattern]
+  int stride = 0;
+  int n_pattern = 0;                    // tiles per mesh
+  int max_h1 = 0;                       // largest own + 1-hop row count
+};
+
 struct DevLevel {
   int V = 0;
   int nnz = 0;
@@ -62,6 +72,13 @@ struct DevLevel {
   const int* tile_meta1_bytes = nullptr;
   int meta1_stride = 0;
   int max_h1 = 0, max_h2 = 0;
+  // Padding-vertex elision: the fake vertices of the binary-tree reorder (lib/coarsening.py:214-258) are isolated in
+  // L~ and share one diagonal value iso_diag, so on them the conv is a dense map with the combined weights
+  // W0 + c W1 + (2c^2 - 1) W2.  real_tiles covers the connected rows (conv path), iso_tiles the isolated ones (plain
+  // GEMM).  n_iso == 0: not applicable on this level.
+  int n_iso = 0;
+  float iso_diag = 0.f;
+  TileSet real_tiles, iso_tiles;
 };
 
 // 2-tap channel resampling table (F.interpolate(mode='linear', align_corners=False) along channels,
@@ -199,6 +216,8 @@ struct UmmaConvArgs {
   // (head_wt = k_thin_prep's [64][12] table); y is then not written at all
   const float* head_wt = nullptr;
   float* head_z = nullptr;
+  // optional: run on this tile family instead of the level's consecutive 128-row tiles (T1-given and plain mode)
+  const TileSet* tiles = nullptr;
 };
 // Host: build the per-tile halo metadata of one level (uploads; device pointers appended to `owned`).
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
@@ -217,7 +236,11 @@ bool umma_dw_supported(const DevLevel& g, int fin, int fout);
 int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout, const float* dz,
                    const float* a_scale, float* dw_ref, int* status, int sm_count, cudaStream_t s);
 // T1 = L~ x for all rows of a level (tile-staged gather), t1 [batch*V, fin] fp32
-int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s);
+int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s,
+                   const TileSet* tiles = nullptr);
+// K-blocks of the combined weights of the isolated rows: B[n][f] = W[n][3f] + c W[n][3f+1] + (2c^2 - 1) W[n][3f+2]
+// (W in the reference layout [fout, fin*3]); same image as launch_umma_pack_plain(N = fout, K = fin)
+int launch_umma_pack_iso(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s);
 int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
 
 }  // namespace p2m

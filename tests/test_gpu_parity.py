@@ -242,6 +242,30 @@ def test_full_size_smpl_eval_against_oracle(precision):
     assert per_mesh_rel_err(y[pick], yo) < TOL_Y
     real = torch.as_tensor(np.asarray(perm_rev[:n]))
     assert per_mesh_rel_err(y[pick][:, real], yo[:, real]) < TOL_Y   # the 6890 real vertices (base.py:130)
+    if precision == "fp16x3":
+        # Padding-vertex elision (on by default where >= 40 % of a level's rows are isolated: the two finest levels
+        # here): off, and forced on every level that has the tile families, must agree with the default; also in
+        # train mode (BatchNorm statistics run over all rows, elided or not).
+        hier, d = model._hier, torch.cuda.current_device()
+        try:
+            res = {}
+            for mode in (0, 2):
+                hier.set_debug(d, elide_padding=mode)
+                with torch.no_grad():
+                    model.eval()
+                    y_eval = model(x.to(dev()))
+                    model.train()
+                    y_train = model(x[:8].to(dev()))
+                model.load_state_dict(sd)  # undo the running-stat update
+                model.eval()
+                res[mode] = (y_eval, y_train)
+            assert hier.kernel_status(d) == 0
+            assert per_mesh_rel_err(res[0][0], y) < 2e-5
+            assert per_mesh_rel_err(res[2][0], y) < 2e-5
+            assert per_mesh_rel_err(res[2][0][pick], yo) < TOL_Y
+            assert per_mesh_rel_err(res[2][1], res[0][1]) < 2e-5
+        finally:
+            hier.set_debug(d, elide_padding=1)
 
 
 @pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
