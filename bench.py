@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fwd|train] [--batch 256] [--precision fp16x3|fp32]
     python bench.py --impl reference ...     # the reference algorithm on the host cores (oracle port)
+    python bench.py --elide-padding 0|1|2    # ablation of the padding-vertex elision (default: library default = 1)
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): batch 256 synthetic H36M 17-joint poses [256,17,5] ~ N(0,1),
