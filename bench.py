@@ -11,8 +11,12 @@ full coarse-to-fine MeshNet forward (eval mode, randomised BatchNorm running sta
 weights under torch.manual_seed(123)) on a synthetic 6890-vertex genus-0 mesh whose hierarchy has the
 real SMPL level sizes 12288/6144/.../96 (mesh seed 2; SMPL's topology is licence-gated).
 One "step" = one forward over one batch of 256 poses per GPU; N GPUs = N independent shards of a
-256*N batch (weak scaling, no data-path collective).  `--mode train` times forward+backward with an
-L1 loss to random targets plus the single NCCL all-reduce of the flat gradient (configs[2]/[4]).
+256*N batch (weak scaling, no data-path collective).  The same line carries a `train` object: the
+training step of configs[2]/[4] at the same N — forward+backward with an L1 loss to random targets at
+B=256 per GPU plus the single NCCL all-reduce of the flat gradient (the path's only exchange step,
+SURVEY.md §8e), device-timed, max over ranks, with the all-reduce's own device time — so the driver's
+1/2/4/8 runs also record the north-star multi-GPU configuration.  `--mode train` makes that step the
+headline instead (and `--train-steps 0` skips the train object).
 
 Printed JSON (one line, rank 0): see the task contract — `value` is device-timed whole-job meshes/s
 with inputs resident in HBM; `e2e` is the same metric through the C-ABI host entry point
@@ -51,6 +55,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not replay the forward from a CUDA graph")
     ap.add_argument("--elide-padding", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="ablation: p2m_debug_set_elide_padding level (-1 = library default)")
+    ap.add_argument("--train-steps", type=int, default=5,
+                    help="timed steps of the `train` object of a forward run (0 = skip it)")
+    ap.add_argument("--ref-sample", type=int, default=32, help="--impl reference: meshes per step (bounded sample)")
     ap.add_argument("--mesh", default="smpl", choices=["smpl", "mano"],
                     help="smpl: 6890-vertex SMPL-size hierarchy (default, BASELINE configs[1,2,4]); "
                          "mano: 778-vertex MANO-size hierarchy 1088..68, 21 joints (configs[3], use --batch 1024)")
@@ -183,36 +190,44 @@ def cpu_port_meshes_per_s(graph_L, sample, threads=None):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on all host
-    threads; each step is a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: /root/reference does not
+    exist on the GPU box) on the host threads it can use; each step is a bounded sample of the 256-pose batch.
+    Nothing of the product is imported here — the hierarchy comes from oracle.graph_oracle — so that the arm's process
+    never maps libp2m_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    graph_L, _ = build_problem()
+    from oracle import graph_oracle as go
     from oracle import meshnet_oracle as mo
 
+    face = go.synthetic_sphere_faces(MESH["n_vertex"], MESH["seed"])
+    _, graph_L, _, _ = go.build_coarse_graphs(face, 17, go.H36M_SKELETON, go.H36M_FLIP_PAIRS, levels=MESH["levels"])
     laps = mo.laplacians_to_torch(graph_L)
     torch.manual_seed(123)
     sd = mo.randomize_bn_(mo.init_state_dict(5, 3, [m.shape[0] for m in laps], False), seed=7)
-    sample = 8
-    g = torch.Generator().manual_seed(0)
+    sample = max(1, min(args.ref_sample, args.batch))
+    g = torch.Generator().manual_seed(1000)
     x = torch.randn(sample, 17, 5, generator=g)
     cores = best_thread_count(lambda: mo.forward(sd, laps, x[:2], training=False))
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(args.warmup):
             mo.forward(sd, laps, x[:2], training=False)
-        steps = max(1, min(args.steps, 6))
         t0 = time.perf_counter()
-        for _ in range(steps):
+        for _ in range(args.steps):
             mo.forward(sd, laps, x, training=False)
         dt = time.perf_counter() - t0
-    v = sample * steps / dt
+    v = sample * args.steps / dt
+    assert not any("libp2m_b200" in ln for ln in open("/proc/self/maps")), "reference arm mapped the product library"
     line = {"impl": "reference", "metric": "SMPL meshes/sec", "value": v, "unit": "meshes/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{sample} meshes per step (bounded sample of the 256-pose batch)"},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch,
+                       "mesh": "synthetic genus-0, 6890 verts, seed 2", "levels": [int(m.shape[0]) for m in graph_L],
+                       "precision": "fp32 (torch CPU kernels)",
+                       "sample": f"each step = {sample} of the {args.batch} meshes of a batch (bounded sample; the "
+                                 "per-mesh cost of the eval forward does not depend on the batch size)"},
             "cpu_baseline": {"value": v, "unit": "meshes/s", "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
-                             "sample": f"{steps} x {sample} meshes, eval forward, CPU oracle (torch CPU kernels)"},
+                             "sample": f"{args.steps} x {sample} meshes, eval forward, CPU oracle (torch CPU kernels)"},
             "e2e": {"value": v, "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -236,6 +251,76 @@ def capture_stdout():
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+
+
+def measure_train(model, x_host, dev, B, world, rank, steps, warmup, flush, barrier):
+    """configs[2]/[4]: forward + backward (L1 loss to random targets, train-mode BatchNorm, B per GPU) + the single
+    all-reduce of the flat gradient.  Device-timed per step (CUDA events), max over ranks; the all-reduce is also
+    timed on its own (events around the collective: it runs after backward on the same stream, i.e. fully exposed)."""
+    import torch.distributed as dist
+
+    from pose2mesh_release_b200.dist import DataParallelStep
+
+    model.train()
+    dp = DataParallelStep(model)
+    x = x_host.to(dev)
+    tgt = torch.randn(B, model.num_vertices, 3, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+
+    def launch(ev=None):
+        dp.zero_grad()
+        loss = (model(x) - tgt).abs().mean()
+        loss.backward()
+        if ev is not None:
+            ev[0].record()
+        dp.reduce_gradients()
+        if ev is not None:
+            ev[1].record()
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        launch()
+    barrier()
+    from pose2mesh_release_b200 import _lib
+
+    _lib.load().p2m_launch_count_reset()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    for i in range(steps):
+        flush.zero_()
+        evs[i][0].record()
+        launch(evs[i][2:])
+        evs[i][1].record()
+    barrier()
+    launches = int(_lib.load().p2m_launch_count())
+    step_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    ar_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
+    t = torch.tensor([step_ms, ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, ar_ms = float(t[0].item()) / steps, float(t[1].item()) / steps
+    # end to end: host poses in, host loss out, wall clock
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        xs = x_host.to(dev, non_blocking=True)
+        dp.zero_grad()
+        loss = (model(xs) - tgt).abs().mean()
+        loss.backward()
+        dp.reduce_gradients()
+        loss.item()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    grad_bytes = int(dp.flat.grad.numel() * 4)
+    return {"metric": "SMPL meshes/sec (fwd+bwd train step, one gradient all-reduce)", "value": B * world / (step_ms * 1e-3),
+            "unit": "meshes/s", "ms_per_step": step_ms, "steps": steps, "batch_per_gpu": B, "global_batch": B * world,
+            "gpu_launches": launches, "gpu_launches_per_step": launches // max(steps, 1),
+            "allreduce_ms": ar_ms if world > 1 else 0.0, "allreduce_bytes": grad_bytes if world > 1 else 0,
+            "allreduce": (f"one NCCL all_reduce(SUM) of the flat fp32 gradient ({grad_bytes / 1e6:.1f} MB) + 1/world scale per "
+                          "step, issued after backward on the same stream (exposed time = allreduce_ms)") if world > 1
+                         else "single GPU: no collective",
+            "allreduce_busbw_GBps": (2.0 * (world - 1) / world * grad_bytes / (ar_ms * 1e-3) * 1e-9) if world > 1 and ar_ms > 0 else None,
+            "e2e": {"value": B * world * steps / float(tt.item()), "unit": "meshes/s",
+                    "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4}}
 
 
 def main():
@@ -283,44 +368,57 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.mode == "train":
+        # the training step as the headline (profiles/: bench.py --mode train)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            sampler.mark()
+        tr = measure_train(model, x_host, dev, B, world, rank, args.steps, args.warmup, flush, barrier)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            emit({"metric": "SMPL meshes/sec (fwd+bwd train step)", "value": tr["value"], "unit": "meshes/s", "n_gpus": world,
+                  "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"],
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                  "dtype": "f32 (tcgen05 fp16x3 split, fp32 accumulate)" if args.precision == "fp16x3" else "f32",
+                  "data": "synthetic",
+                  "config": {"workload": "configs[2]/[4]: B=256/GPU fwd+bwd, L1 loss, train-mode BatchNorm, one NCCL "
+                                         "all-reduce of the flat gradient" if args.mesh == "smpl" else
+                                         "configs[3]: MANO-size hierarchy 1088..68, 21 joints, forward+backward, L1 loss",
+                             "batch_per_gpu": B, "global_batch": B * world, "levels": [int(m.shape[0]) for m in graph_L],
+                             "precision": args.precision, "parallelism": f"dp{world} (single all-reduce per step)",
+                             "l2": "256 MiB buffer written between timed iterations (outside the event pairs)"},
+                  "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"], "gpu_launches_per_step": tr["gpu_launches_per_step"],
+                  "clocks": clocks, "train": tr})
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     step_graph = None
-    if args.mode == "fwd":
-        model.eval()
+    model.eval()
 
-        def step():
-            with torch.no_grad():
-                return model(x)
+    def step():
+        with torch.no_grad():
+            return model(x)
 
-        launch = step
-        if not args.no_graph:
-            # replay the ~100-launch forward from a CUDA graph (the library only enqueues on the current stream)
-            try:
-                side = torch.cuda.Stream()
-                with torch.cuda.stream(side):
-                    step()
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    y_static = step()
-                torch.cuda.synchronize()
-                step_graph, launch = graph, graph.replay
-            except Exception as e:  # keep the bench alive; say so in the JSON
-                sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); running eagerly\n")
-                torch.cuda.synchronize()
-                step_graph, launch = None, step
-    else:
-        from pose2mesh_release_b200.dist import DataParallelStep
-
-        model.train()
-        dp = DataParallelStep(model)
-        tgt = torch.randn(B, model.num_vertices, 3, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
-
-        def launch():
-            dp.zero_grad()
-            loss = (model(x) - tgt).abs().mean()
-            loss.backward()
-            dp.reduce_gradients()
-            return loss
+    launch = step
+    if not args.no_graph:
+        # replay the ~100-launch forward from a CUDA graph (the library only enqueues on the current stream)
+        try:
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y_static = step()  # noqa: F841  (keeps the graph's output alive)
+            torch.cuda.synchronize()
+            step_graph, launch = graph, graph.replay
+        except Exception as e:  # keep the bench alive; say so in the JSON
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); running eagerly\n")
+            torch.cuda.synchronize()
+            step_graph, launch = None, step
 
     for _ in range(max(args.warmup, 3)):
         launch()
@@ -358,39 +456,25 @@ def main():
     else:
         per_step_launches = launches_eager // max(args.steps, 1)
 
-    # ---- end-to-end through the C-ABI host entry point (pinned host in / host out), wall clock
-    e2e = None
-    if args.mode == "fwd":
-        model.eval()
-        y_host = torch.empty((B, model.num_vertices, 3), dtype=torch.float32).pin_memory()
-        for _ in range(2):
-            model.forward_host(x_host, out=y_host)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            model.forward_host(x_host, out=y_host)      # synchronises its stream before returning
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * args.steps / float(tt.item()), "unit": "meshes/s",
-               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4)}
-    else:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            xs = x_host.to(dev, non_blocking=True)
-            dp.zero_grad()
-            loss = (model(xs) - tgt).abs().mean()
-            loss.backward()
-            dp.reduce_gradients()
-            loss_host = loss.item()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * args.steps / float(tt.item()), "unit": "meshes/s",
-               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4}
+    # ---- end to end through the C-ABI host entry point, wall clock: pinned host poses in, host vertices out.  The call
+    # is p2m_meshnet_forward_vertices_host: the callers' gather pred[:, perm_reverse[:6890]] (lib/core/base.py:130,201)
+    # is fused into the head layer, so what travels back is what the reference's callers keep of a mesh.
+    n_real = MESH["n_vertex"] if args.mesh == "smpl" else 778
+    y_host = torch.empty((B, n_real, 3), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        model.forward_host(x_host, out=y_host, perm_reverse=perm_rev, n_vertex=n_real)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.forward_host(x_host, out=y_host, perm_reverse=perm_rev, n_vertex=n_real)   # synchronises its stream
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = {"value": B * world * args.steps / float(tt.item()), "unit": "meshes/s",
+           "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
+           "call": "p2m_meshnet_forward_vertices_host (fused perm_reverse gather: [B, 6890, 3] back to the host)"}
 
     # ---- roofline of the dominant kernel: per-layer CUDA events inside the eval forward
     roofline, layers = None, None
@@ -446,6 +530,12 @@ def main():
                         "sample": f"{args.cpu_sample} meshes, eval forward, CPU oracle (torch CPU kernels), {dt:.1f} s; "
                                   f"thread count = fastest of 8/16/32/64/all"}
 
+    used_graph = step_graph is not None
+    train = None
+    if args.train_steps > 0 and args.mesh == "smpl":
+        del step_graph, launch
+        train = measure_train(model, x_host, dev, B, world, rank, args.train_steps, 3, flush, barrier)
+
     if rank == 0:
         line = {
             "metric": "SMPL meshes/sec" if args.mode == "fwd" else "SMPL meshes/sec (fwd+bwd train step)",
@@ -464,9 +554,9 @@ def main():
                        "parallelism": f"dp{world} (independent shards, no data-path collective)" if args.mode == "fwd"
                        else f"dp{world} (single all-reduce per step)",
                        "l2": "256 MiB buffer written between timed iterations (outside the event pairs)",
-                       "cuda_graph": step_graph is not None},
+                       "cuda_graph": used_graph},
             "e2e": e2e, "gpu_launches": int(per_step_launches * args.steps), "gpu_launches_per_step": int(per_step_launches),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "layers": layers,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "train": train, "layers": layers,
         }
         emit(line)
     if world > 1:

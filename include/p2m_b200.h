@@ -9,9 +9,10 @@
  * on: plain pointers and sizes, no torch types.  All `const float*` / `float*` data arguments are
  * DEVICE pointers owned by the caller unless a function name ends in `_host`.  Every function
  * returns 0 on success or a non-zero p2m_status; p2m_last_error() gives the message (thread-local).
- * Nothing here throws or aborts, and the library keeps no global mutable state besides per-handle
- * device buffers, so one handle per device can be driven from concurrent threads
- * (nn.DataParallel, lib/core/base.py:108).
+ * Nothing here throws or aborts, and the library keeps no global mutable state (per-handle device
+ * buffers and thread-local error / launch-count bookkeeping only), so one handle per device can be
+ * driven from concurrent threads (nn.DataParallel, lib/core/base.py:108).  Entry points that touch
+ * the device make the handle's device current for their own duration and restore the caller's.
  */
 #ifndef P2M_B200_H_
 #define P2M_B200_H_
@@ -84,11 +85,15 @@ int p2m_model_set_precision(p2m_model_t* m, int precision);
  * every conv layer; p2m_model_layer_times_ms returns the last forward's per-layer device times.      */
 int p2m_model_set_profiling(p2m_model_t* m, int enable);
 int p2m_model_layer_times_ms(p2m_model_t* m, float* out_ms, int n);
-/* Debug: device-synchronises and returns the status word of the tcgen05 kernels (0 = no mbarrier
- * wait ever timed out; otherwise the id of the wait that did).                                      */
+/* Every mbarrier wait of the tcgen05 kernels is time-bounded (2 s).  A kernel whose wait expired records the
+ * wait's id in a per-handle status word the host can read without a copy; the NEXT entry point called on
+ * the handle (and p2m_meshnet_forward_host itself, after its stream synchronisation) then fails with
+ * P2M_ERR_CUDA and clears the word — results of a timed-out kernel are never returned silently.
+ * p2m_debug_kernel_status device-synchronises and returns the word without clearing it (0 = clean).  */
 int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out);
-/* Debug: CTA 0 of the tcgen05 kernels logs (event << 48 | SM clock) into dev_buf [8][512] int64; NULL = off. */
-int p2m_debug_set_trace(void* dev_buf);
+/* Debug (libraries built with -DP2M_UMMA_TRACE only; P2M_ERR_INVALID otherwise): CTA 0 of this handle's
+ * tcgen05 conv kernels logs (event << 48 | SM clock) into dev_buf [8][512] int64; NULL = off.        */
+int p2m_debug_set_trace(p2m_model_t* m, void* dev_buf);
 /* Debug / ablation: 1 (default) = T1 = L~x as a separate pass + conv with given T1; 0 = fully fused conv.   */
 int p2m_debug_set_split_t1(p2m_model_t* m, int enable);
 /* Debug / ablation: 1 (default) = in eval mode the 128->64 conv's epilogue produces the 64->3 head's projections
@@ -131,6 +136,11 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* params, const p2m_p
 size_t p2m_meshnet_host_io_bytes(const p2m_model_t* m, int batch);
 int p2m_meshnet_forward_host(p2m_model_t* m, const p2m_params_t* params, const float* x_host, float* y_host,
                              int batch, void* workspace, size_t workspace_bytes, p2m_stream_t stream);
+/* Same with the fused output gather (p2m_model_set_output_gather): y_vertices_host is [B, n_slots, Cout], i.e. what
+ * the reference's callers keep of a mesh (lib/core/base.py:130,201; demo/run.py:170) — 6890 of the 12288 rows.   */
+int p2m_meshnet_forward_vertices_host(p2m_model_t* m, const p2m_params_t* params, const float* x_host,
+                                      float* y_vertices_host, int batch, void* workspace, size_t workspace_bytes,
+                                      p2m_stream_t stream);
 
 /* ---- single Chebyshev graph convolution ----------------------------------------------------------
  * graph_conv_cheby (cheby_graph_conv.py:5-42) on hierarchy level `level`:

@@ -35,6 +35,7 @@ class _Cfg:
     class MODEL:
         posenet_pretrained = False
         posenet_path = ""
+        input_shape = (384, 288)   # lib/core/config.py:52
 
 
 _loaded = None

@@ -14,6 +14,18 @@ LIB_PATH = os.path.join(_HERE, "libp2m_b200.so")
 
 P2M_PREC_FP32_SIMT = 0
 P2M_PREC_FP16X3_TC = 1
+PRECISIONS = {"fp32": P2M_PREC_FP32_SIMT, "fp16x3": P2M_PREC_FP16X3_TC}
+
+
+def default_precision() -> int:
+    """Precision of new modules / graph handles: the tcgen05 path (fp16x3: error-compensated split, fp32
+    accumulate, 1e-4 parity like the fp32 path) unless the environment says ``P2M_PRECISION=fp32`` (the CUDA-core
+    escape hatch for activations beyond fp16's range).  A drop-in user (install.py) therefore gets the fast path
+    without touching the module; ``Pose2Mesh.set_precision`` / ``set_default_precision`` still override it."""
+    name = os.environ.get("P2M_PRECISION", "fp16x3").strip().lower()
+    if name not in PRECISIONS:
+        raise RuntimeError(f"P2M_PRECISION={name!r}: expected one of {sorted(PRECISIONS)}")
+    return PRECISIONS[name]
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
@@ -73,7 +85,7 @@ class ConvBwdArgs(C.Structure):
 EXPORTS = [
     "p2m_model_create", "p2m_model_destroy", "p2m_model_num_layers", "p2m_model_layer_info",
     "p2m_model_set_precision", "p2m_debug_kernel_status", "p2m_debug_set_trace", "p2m_debug_set_split_t1", "p2m_debug_set_fuse_head", "p2m_debug_set_elide_padding", "p2m_model_set_profiling", "p2m_model_layer_times_ms", "p2m_meshnet_workspace_bytes", "p2m_meshnet_backward_scratch_bytes",
-    "p2m_meshnet_forward", "p2m_meshnet_backward", "p2m_model_set_output_gather", "p2m_meshnet_forward_vertices", "p2m_meshnet_host_io_bytes", "p2m_meshnet_forward_host",
+    "p2m_meshnet_forward", "p2m_meshnet_backward", "p2m_model_set_output_gather", "p2m_meshnet_forward_vertices", "p2m_meshnet_host_io_bytes", "p2m_meshnet_forward_host", "p2m_meshnet_forward_vertices_host",
     "p2m_cheb_conv_workspace_bytes", "p2m_cheb_conv_fwd", "p2m_cheb_conv_bwd", "p2m_graph_match_level",
     "p2m_last_error", "p2m_version", "p2m_launch_count", "p2m_launch_count_reset",
 ]
@@ -116,7 +128,7 @@ def load() -> C.CDLL:
         lib.p2m_debug_set_fuse_head.restype = C.c_int
         lib.p2m_debug_set_elide_padding.argtypes = [vp, C.c_int]
         lib.p2m_debug_set_elide_padding.restype = C.c_int
-        lib.p2m_debug_set_trace.argtypes = [vp]
+        lib.p2m_debug_set_trace.argtypes = [vp, vp]
         lib.p2m_debug_set_trace.restype = C.c_int
         lib.p2m_debug_kernel_status.argtypes = [vp, c_int32_p]
         lib.p2m_debug_kernel_status.restype = C.c_int
@@ -134,6 +146,8 @@ def load() -> C.CDLL:
         lib.p2m_meshnet_forward_vertices.restype = C.c_int
         lib.p2m_meshnet_forward_host.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, vp, sz, vp]
         lib.p2m_meshnet_forward_host.restype = C.c_int
+        lib.p2m_meshnet_forward_vertices_host.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, vp, sz, vp]
+        lib.p2m_meshnet_forward_vertices_host.restype = C.c_int
         lib.p2m_meshnet_backward.argtypes = [vp, C.POINTER(Params), C.POINTER(Params), vp, vp, vp, C.c_int, vp, sz,
                                              vp, sz, vp]
         lib.p2m_meshnet_backward.restype = C.c_int

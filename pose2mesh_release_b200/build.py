@@ -12,6 +12,8 @@ LIB = os.path.join(HERE, "libp2m_b200.so")
 SOURCES = ["p2m_api.cu", "kernels_simt.cu", "cheb_umma.cu", "graph_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+if os.environ.get("P2M_TRACE") == "1":  # debug build: per-role event timeline of the tcgen05 conv kernel (tools/umma_trace.py)
+    FLAGS.append("-DP2M_UMMA_TRACE")
 
 
 def _stale() -> bool:

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 _graph_cache = {}
-_default_precision = _lib.P2M_PREC_FP32_SIMT
+_default_precision = _lib.default_precision()
 
 
 def set_default_precision(precision: str):
@@ -102,7 +102,8 @@ def graph_handle(L) -> GraphHandle:
         m = sp.csr_matrix(L)
     gh = GraphHandle(m)
     try:
-        _graph_cache[key] = (weakref.ref(L), gh)
+        # the entry (and with it the handle's device memory) goes away with the Laplacian object
+        _graph_cache[key] = (weakref.ref(L, lambda _r, k=key: _graph_cache.pop(k, None)), gh)
     except TypeError:
         pass
     return gh
@@ -123,7 +124,7 @@ class ChebConvLinear(torch.autograd.Function):
             raise ValueError(f"shape mismatch: x {tuple(x.shape)}, L {gh.V}, weight {tuple(weight.shape)}")
         dev = x.device
         h = gh.handle(dev.index)
-        weight, bias = weight.contiguous(), bias.contiguous()
+        weight, bias = weight.contiguous().float(), bias.contiguous().float()
         y = torch.empty((B, V, fout), device=dev, dtype=torch.float32)
         nbytes = lib.p2m_cheb_conv_workspace_bytes(h, 0, B, fin, fout)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)

@@ -91,45 +91,60 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");                          // so waiting warps do not take issue slots from the loader warps
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU box.  On timeout the CTA-wide abort flag is
-// raised, the global status word is set and every later wait falls through immediately.
+// Bounded wait: a protocol bug must not hang the GPU box.  On timeout (2 s of %globaltimer: three orders of magnitude
+// beyond any legitimate wait, preempted / time-sliced contexts included) the CTA-wide abort flag is raised so that
+// every later wait of this CTA falls through, and the wait's id is written to the model's status word — a word of
+// MAPPED HOST memory, so the host sees it without a copy: every API entry point checks it and fails with
+// P2M_ERR_CUDA (p2m_api.cu: check_kernel_status), i.e. a timed-out kernel never hands results to the caller silently.
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+constexpr unsigned long long MBAR_TIMEOUT_NS = 2000000000ull;
+__device__ __noinline__ void mbar_timeout(volatile int* abort_flag, int* status, int code) {
+  *abort_flag = 1;
+  *reinterpret_cast<volatile int*>(status) = code;
+  __threadfence_system();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status,
                                           int code) {
   if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = global_ns();
-  for (;;) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
 #pragma unroll 1
     for (int it = 0; it < 64; ++it) {
       if (mbar_try_wait(bar, parity)) return;
     }
     if (*abort_flag) return;
-    if (global_ns() - t0 > 400000000ull) break;  // 0.4 s: far beyond any legitimate wait
+    if ((spin & 63u) == 63u) {  // the timer is only consulted every 4096 failed polls (~80 ms of hardware-suspended waits)
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > MBAR_TIMEOUT_NS) break;
+    }
   }
-  *abort_flag = 1;
-  atomicExch(status, code);
+  mbar_timeout(abort_flag, status, code);
 }
 // Same, but with a nanosleep back-off between polls: for the roles whose waits span most of a tile
 // (epilogue, loaders) so that their polling does not steal issue slots from the producers.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status,
                                                   int code) {
   if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = global_ns();
-  for (;;) {
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
 #pragma unroll 1
     for (int it = 0; it < 16; ++it) {
       if (mbar_try_wait(bar, parity)) return;
       __nanosleep(200);
     }
     if (*abort_flag) return;
-    if (global_ns() - t0 > 400000000ull) break;
+    if ((spin & 255u) == 255u) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > MBAR_TIMEOUT_NS) break;
+    }
   }
-  *abort_flag = 1;
-  atomicExch(status, code);
+  mbar_timeout(abort_flag, status, code);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -322,12 +337,18 @@ struct KParams {
   CUtensorMap tm_x, tm_t1;
 };
 
+// Event timeline of CTA 0 (tools/umma_trace.py): compiled in only with -DP2M_UMMA_TRACE (build.py: P2M_TRACE=1);
+// production kernels carry no clock reads.
+#ifdef P2M_UMMA_TRACE
 __device__ __forceinline__ void trace_ev(const KParams& p, int role, int& n, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && n < 512) {
     p.trace[role * 512 + n] = ((long long)ev << 48) | (clock64() & 0xFFFFFFFFFFFFll);
     ++n;
   }
 }
+#else
+__device__ __forceinline__ void trace_ev(const KParams&, int, int&, int) {}
+#endif
 
 // Warp roles (24 warps, one persistent CTA per SM):
 //   0..15  producers: SpMM out of shared memory + fp16 (hi,lo) split + swizzled A-block stores
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       mbar_init(smem_u32(b_acc_empty + s), 4);
     }
     *abort_flag = (smem_u32(ring) & 1023u) ? 1 : 0;
-    if (*abort_flag) atomicExch(p.status, 100);
+    if (*abort_flag) mbar_timeout(abort_flag, p.status, 100);
     fence_barrier_init();
   }
   const float a_scale = p.a_scale ? *p.a_scale : 1.f;
@@ -942,7 +963,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
     mbar_init(smem_u32(b_g_empty), 1);
     mbar_init(smem_u32(b_done), 1);
     *abort_flag = (smem_u32(ring) & 1023u) ? 1 : 0;
-    if (*abort_flag) atomicExch(p.status, 100);
+    if (*abort_flag) mbar_timeout(abort_flag, p.status, 100);
     fence_barrier_init();
   }
   const float a_scale = p.a_scale ? *p.a_scale : 1.f;
@@ -1278,7 +1299,6 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
   *reinterpret_cast<uint4*>(out + (size_t)u * fout * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
 }
 
-long long* g_umma_trace = nullptr;  // debug: set through set_umma_trace()
 // debug: P2M_UMMA_TMA=0 stages every row with cp.async (A/B measurements of the TMA own-row loads)
 const bool g_umma_tma = [] { const char* e = std::getenv("P2M_UMMA_TMA"); return !(e && e[0] == '0'); }();
 
@@ -1376,7 +1396,7 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   p.ldy = a.ldy > 0 ? a.ldy : a.fout;
   p.y_col0 = a.y_col0;
   p.status = status;
-  p.trace = g_umma_trace;
+  p.trace = a.trace;
   p.head_wt = (N == 64) ? a.head_wt : nullptr;
   p.head_z = (N == 64) ? a.head_z : nullptr;
   p.tma = 0;
@@ -1699,7 +1719,6 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
   return P2M_OK;
 }
 
-void set_umma_trace(long long* dev_buf) { g_umma_trace = dev_buf; }
 
 size_t dw_smem_bytes(int XS, const DevLevel& g) {
   return 1024 + (size_t)DW_NS * A_BLOCK_BYTES + DW_G_BYTES + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +

@@ -47,7 +47,9 @@ struct p2m_model {
   std::vector<Block> blocks;
   int n_joint = 0, cin = 0, cout = 0;
   int fc_in = 0, fc_out = 0;
-  int* kernel_status = nullptr;  // device word set by a tcgen05 kernel whose mbarrier wait timed out
+  int* kernel_status = nullptr;       // device alias of status_host (what the kernels write)
+  volatile int* status_host = nullptr;  // mapped pinned host word: set by a tcgen05 kernel whose mbarrier wait timed out
+  long long* trace = nullptr;          // debug (P2M_UMMA_TRACE builds): CTA-0 event log of the tcgen05 conv kernel
   int* out_map = nullptr;        // optional fused output gather (vertex -> slot, -1 = dropped)
   int out_rows = 0;
   float* zero_row = nullptr;     // 128 B of zeros (halo source for the empty slots of ragged tiles)
@@ -62,6 +64,37 @@ struct p2m_model {
 };
 
 namespace {
+
+// Every entry point that touches the device makes the model's device current for its own duration only: the
+// caller's current device is restored on every exit path (single-process multi-GPU callers, nn.DataParallel
+// threads, handles garbage-collected at arbitrary times).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// A tcgen05 kernel whose bounded mbarrier wait expired wrote the wait's id into the mapped host status word
+// (cheb_umma.cu: mbar_timeout).  Checked without any synchronisation at every entry point (and after the stream
+// synchronisation of the *_host entry point): the call fails instead of handing out the results of a kernel
+// that fell through its barriers.  The word is cleared once reported.
+int check_kernel_status(p2m_model* m, const char* where) {
+  if (m->status_host == nullptr) return P2M_OK;
+  const int code = *m->status_host;
+  if (code == 0) return P2M_OK;
+  *m->status_host = 0;
+  set_error(std::string(where) + ": a tcgen05 kernel of an earlier call on this handle timed out on mbarrier wait #" +
+            std::to_string(code) + " (results of that call are invalid)");
+  return P2M_ERR_CUDA;
+}
 
 constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
@@ -249,6 +282,7 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
   if (conv_on_tensor_cores(m, L, wpack)) {
     P2M_TRY(launch_umma_pack_weights(w_ref, L.fin, L.fout, wpack, s));
     UmmaConvArgs a;
+    a.trace = m->trace;
     a.head_wt = head_wt;
     a.head_z = head_z;
     // Padding-vertex elision (DevLevel::n_iso): connected rows through the conv on index-list tiles, isolated rows
@@ -346,7 +380,7 @@ int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
               ", this library is built for sm_100a only");
     return P2M_ERR_NOGPU;
   }
-  P2M_CUDA_OK(cudaSetDevice(d->device));
+  DeviceGuard guard(d->device);
   p2m_model* m = new p2m_model();
   m->device = d->device;
   m->sm_count = prop.multiProcessorCount;
@@ -379,14 +413,21 @@ int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
     m->levels.push_back(g);
   }
   {
-    std::vector<int> zero(1, 0);
     std::vector<float> zrow(64, 0.f);
-    int st = upload(m, zero, &m->kernel_status);
-    if (!st) st = upload(m, zrow, &m->zero_row);
+    int st = upload(m, zrow, &m->zero_row);
+    void* hp = nullptr;
+    if (!st && (cudaHostAlloc(&hp, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+                cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->kernel_status), hp, 0) != cudaSuccess)) {
+      set_error("model_create: cannot allocate the mapped status word");
+      if (hp) cudaFreeHost(hp);
+      st = P2M_ERR_CUDA;
+    }
     if (st) {
       p2m_model_destroy(m);
       return st;
     }
+    m->status_host = static_cast<volatile int*>(hp);
+    *m->status_host = 0;
   }
   // ---- plan (meshnet.py:21-33, 86-94)
   const int nb = d->n_blocks;
@@ -463,8 +504,9 @@ int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
 
 void p2m_model_destroy(p2m_model_t* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  DeviceGuard guard(m->device);
   for (void* p : m->owned) cudaFree(p);
+  if (m->status_host) cudaFreeHost(const_cast<int*>(m->status_host));
   for (cudaEvent_t e : m->ev_beg) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_end) cudaEventDestroy(e);
   delete m;
@@ -487,18 +529,24 @@ int p2m_debug_kernel_status(p2m_model_t* m, int32_t* out) {
     set_error("debug_kernel_status: bad argument");
     return P2M_ERR_INVALID;
   }
-  P2M_CUDA_OK(cudaSetDevice(m->device));
+  DeviceGuard guard(m->device);
   P2M_CUDA_OK(cudaDeviceSynchronize());
-  int v = 0;
-  P2M_CUDA_OK(cudaMemcpy(&v, m->kernel_status, sizeof(int), cudaMemcpyDeviceToHost));
-  *out = v;
+  *out = m->status_host ? *m->status_host : 0;
   return P2M_OK;
 }
 
-// Debug: route the tcgen05 kernel's CTA-0 event log into `dev_buf` (device, 8*512 int64) or disable (NULL).
-int p2m_debug_set_trace(void* dev_buf) {
-  set_umma_trace(static_cast<long long*>(dev_buf));
+// Debug: route the tcgen05 conv kernel's CTA-0 event log into `dev_buf` (device, 8*512 int64) or disable (NULL).
+// Only in libraries built with -DP2M_UMMA_TRACE (P2M_TRACE=1 python -m pose2mesh_release_b200.build --force).
+int p2m_debug_set_trace(p2m_model_t* m, void* dev_buf) {
+  if (!m) return P2M_ERR_INVALID;
+#ifdef P2M_UMMA_TRACE
+  m->trace = static_cast<long long*>(dev_buf);
   return P2M_OK;
+#else
+  if (dev_buf == nullptr) return P2M_OK;
+  set_error("debug_set_trace: this library was built without P2M_UMMA_TRACE");
+  return P2M_ERR_INVALID;
+#endif
 }
 
 // Debug / ablation: 1 (default) = two-pass tcgen05 conv (k_cheb_t1 + conv with given T1), 0 = fully fused conv.
@@ -523,7 +571,7 @@ int p2m_model_set_profiling(p2m_model_t* m, int enable) {
     set_error("set_profiling: bad argument");
     return P2M_ERR_INVALID;
   }
-  P2M_CUDA_OK(cudaSetDevice(m->device));
+  DeviceGuard guard(m->device);
   if (enable && m->ev_beg.empty()) {
     m->ev_beg.resize(m->layers.size());
     m->ev_end.resize(m->layers.size());
@@ -541,7 +589,7 @@ int p2m_model_layer_times_ms(p2m_model_t* m, float* out, int n) {
     set_error("layer_times_ms: profiling was not enabled or buffer too small");
     return P2M_ERR_INVALID;
   }
-  P2M_CUDA_OK(cudaSetDevice(m->device));
+  DeviceGuard guard(m->device);
   for (size_t i = 0; i < m->layers.size(); ++i) {
     P2M_CUDA_OK(cudaEventSynchronize(m->ev_end[i]));
     P2M_CUDA_OK(cudaEventElapsedTime(&out[i], m->ev_beg[i], m->ev_end[i]));
@@ -579,6 +627,8 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
     return P2M_ERR_INVALID;
   }
   P2M_TRY(check_params(m, P, true));
+  P2M_TRY(check_kernel_status(m, "meshnet_forward"));
+  DeviceGuard guard(m->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   WsMap w = map_workspace(m, B, training, workspace);
   if (w.bytes > workspace_bytes) {
@@ -739,8 +789,14 @@ int p2m_model_set_output_gather(p2m_model_t* m, const int32_t* vertex_of_slot, i
     }
     map[v] = j;
   }
-  P2M_CUDA_OK(cudaSetDevice(m->device));
-  P2M_TRY(upload(m, map, &m->out_map));
+  DeviceGuard guard(m->device);
+  if (m->out_map == nullptr) {  // one [V0] map per handle, overwritten in place by later calls
+    P2M_TRY(upload(m, map, &m->out_map));
+  } else {
+    // earlier forwards may still be reading the old map on their streams
+    P2M_CUDA_OK(cudaDeviceSynchronize());
+    P2M_CUDA_OK(cudaMemcpy(m->out_map, map.data(), sizeof(int) * V0, cudaMemcpyHostToDevice));
+  }
   m->out_rows = n_slots;
   return P2M_OK;
 }
@@ -754,28 +810,41 @@ int p2m_meshnet_forward_vertices(p2m_model_t* m, const p2m_params_t* P, const fl
   return meshnet_forward_impl(m, P, x, y_vertices, B, 0, workspace, workspace_bytes, stream, 1);
 }
 
-int p2m_meshnet_forward_host(p2m_model_t* m, const p2m_params_t* P, const float* x_host, float* y_host, int B,
-                             void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
-  if (!m || !x_host || !y_host || B <= 0 || !workspace || m->layers.empty()) {
-    set_error("meshnet_forward_host: bad argument");
+static int forward_host_impl(p2m_model_t* m, const p2m_params_t* P, const float* x_host, float* y_host, int B,
+                             void* workspace, size_t workspace_bytes, p2m_stream_t stream, int gathered) {
+  if (!m || !x_host || !y_host || B <= 0 || !workspace || m->layers.empty() || (gathered && !m->out_map)) {
+    set_error(gathered && m && !m->out_map ? "meshnet_forward_vertices_host: call p2m_model_set_output_gather first"
+                                           : "meshnet_forward_host: bad argument");
     return P2M_ERR_INVALID;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t xb = (size_t)B * m->n_joint * m->cin * 4, yb = (size_t)B * m->levels[0].V * m->cout * 4;
+  const size_t out_rows = gathered ? (size_t)m->out_rows : (size_t)m->levels[0].V;
+  const size_t xb = (size_t)B * m->n_joint * m->cin * 4, yb = (size_t)B * out_rows * m->cout * 4;
   const size_t io = p2m_meshnet_host_io_bytes(m, B);
   const size_t need = p2m_meshnet_workspace_bytes(m, B, 0);
   if (workspace_bytes < need + io) {
     set_error("meshnet_forward_host: workspace too small");
     return P2M_ERR_WORKSPACE;
   }
+  DeviceGuard guard(m->device);
   char* base = static_cast<char*>(workspace);
   float* xd = reinterpret_cast<float*>(base + need);
   float* yd = reinterpret_cast<float*>(base + need + align_up(xb));
   P2M_CUDA_OK(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, s));
-  P2M_TRY(p2m_meshnet_forward(m, P, xd, yd, B, 0, workspace, need, stream));
+  P2M_TRY(meshnet_forward_impl(m, P, xd, yd, B, 0, workspace, need, stream, gathered));
   P2M_CUDA_OK(cudaMemcpyAsync(y_host, yd, yb, cudaMemcpyDeviceToHost, s));
   P2M_CUDA_OK(cudaStreamSynchronize(s));
-  return P2M_OK;
+  return check_kernel_status(m, "meshnet_forward_host");
+}
+
+int p2m_meshnet_forward_host(p2m_model_t* m, const p2m_params_t* P, const float* x_host, float* y_host, int B,
+                             void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  return forward_host_impl(m, P, x_host, y_host, B, workspace, workspace_bytes, stream, 0);
+}
+
+int p2m_meshnet_forward_vertices_host(p2m_model_t* m, const p2m_params_t* P, const float* x_host, float* y_vertices_host,
+                                      int B, void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  return forward_host_impl(m, P, x_host, y_vertices_host, B, workspace, workspace_bytes, stream, 1);
 }
 
 // -------------------------------------------------------------------------------------
@@ -788,6 +857,8 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params
   }
   P2M_TRY(check_params(m, P, false));
   P2M_TRY(check_params(m, G, false));
+  P2M_TRY(check_kernel_status(m, "meshnet_backward"));
+  DeviceGuard guard(m->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   WsMap w = map_workspace(m, B, 1, workspace);
   BwdMap sc = map_scratch(m, B, scratch);
@@ -934,6 +1005,8 @@ int p2m_cheb_conv_fwd(p2m_model_t* m, const p2m_conv_fwd_args_t* a, void* worksp
     set_error("cheb_conv_fwd: workspace too small");
     return P2M_ERR_WORKSPACE;
   }
+  P2M_TRY(check_kernel_status(m, "cheb_conv_fwd"));
+  DeviceGuard guard(m->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Layer L{};
   L.level = a->level;
@@ -992,6 +1065,8 @@ int p2m_cheb_conv_bwd(p2m_model_t* m, const p2m_conv_bwd_args_t* a, void* worksp
     set_error("cheb_conv_bwd: workspace too small");
     return P2M_ERR_WORKSPACE;
   }
+  P2M_TRY(check_kernel_status(m, "cheb_conv_bwd"));
+  DeviceGuard guard(m->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const DevLevel& g = m->levels[a->level];
   const int fin = a->fin, fout = a->fout;

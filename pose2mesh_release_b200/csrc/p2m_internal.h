@@ -218,11 +218,11 @@ struct UmmaConvArgs {
   float* head_z = nullptr;
   // optional: run on this tile family instead of the level's consecutive 128-row tiles (T1-given and plain mode)
   const TileSet* tiles = nullptr;
+  long long* trace = nullptr;       // debug (P2M_UMMA_TRACE builds only): [8][512] event log of CTA 0
 };
 // Host: build the per-tile halo metadata of one level (uploads; device pointers appended to `owned`).
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
                           std::vector<void*>* owned);
-void set_umma_trace(long long* dev_buf);  // debug: [8][512] event log of CTA 0, or nullptr
 bool umma_conv_supported(const DevLevel& g, int fin, int fout);
 size_t umma_wpack_bytes(int fin, int fout);
 int launch_umma_pack_weights(const float* W /*[fout, fin*3] ref layout*/, int fin, int fout, void* wpack, cudaStream_t s);

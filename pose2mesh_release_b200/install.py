@@ -12,8 +12,27 @@ tree is modified on disk.
 from __future__ import annotations
 
 import importlib
+import sys
 
 _saved = {}
+_rebound = []  # (module, attribute, original) for `from graph_utils import build_coarse_graphs`-style holders
+
+
+def _rebind_holders(original, replacement):
+    """Modules imported BEFORE install() that did ``from graph_utils import build_coarse_graphs`` (the
+    reference's datasets and demo/run.py do) hold their own reference to the original function: patch
+    those bindings too, so that the overlay is never half applied."""
+    for name, mod in list(sys.modules.items()):
+        if mod is None or name.startswith("pose2mesh_release_b200"):
+            continue
+        try:
+            items = list(vars(mod).items())
+        except TypeError:
+            continue
+        for attr, val in items:
+            if val is original:
+                setattr(mod, attr, replacement)
+                _rebound.append((mod, attr, original))
 
 
 def install(replace_graph_builder: bool = True):
@@ -32,10 +51,15 @@ def install(replace_graph_builder: bool = True):
     if replace_graph_builder:
         ref_gu = importlib.import_module("graph_utils")
         _saved.setdefault("graph", ref_gu.build_coarse_graphs)
+        _rebind_holders(_saved["graph"], my_graph.build_coarse_graphs)   # includes graph_utils itself
         ref_gu.build_coarse_graphs = my_graph.build_coarse_graphs
+    _rebind_holders(_saved["conv"], my_conv.graph_conv_cheby)
 
 
 def uninstall():
+    while _rebound:
+        mod, attr, original = _rebound.pop()
+        setattr(mod, attr, original)
     if "meshnet" in _saved:
         ref_meshnet = importlib.import_module("models.meshnet")
         ref_meshnet.Pose2Mesh, ref_meshnet.get_model, ref_meshnet.graph_conv_cheby = _saved.pop("meshnet")

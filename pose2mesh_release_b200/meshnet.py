@@ -62,7 +62,7 @@ class BakedHierarchy:
         self.block_chans = np.array([c for p in plan for c in p], dtype=np.int32)
         self._handles = {}
         self._lock = threading.Lock()
-        self.precision = _lib.P2M_PREC_FP32_SIMT
+        self.precision = _lib.default_precision()
 
     def handle(self, device_index: int) -> int:
         with self._lock:
@@ -196,13 +196,18 @@ class _MeshNetFunction(torch.autograd.Function):
             ctx.hier, ctx.n_layers, ctx.ws, ctx.ws_bytes = hier, n_layers, ws, ws_bytes
             ctx.save_for_backward(x, *params)
         ctx.differentiable = needs_grad
+        ctx.training = training
         return y
 
     @staticmethod
     def backward(ctx, dy):
         if not ctx.differentiable:
             raise RuntimeError("pose2mesh_release_b200: backward through an eval-mode MeshNet forward is not "
-                               "supported (BatchNorm was folded); call .train() first")
+                               "supported (BatchNorm was folded into the conv epilogues and no activations were "
+                               "kept); call .train() first")
+        if ctx.ws is None:
+            raise RuntimeError("pose2mesh_release_b200: the saved activations of this forward were already released "
+                               "by an earlier backward (retain_graph is not supported: run the forward again)")
         lib = _lib.load()
         x, *params = ctx.saved_tensors
         n_layers, hier = ctx.n_layers, ctx.hier
@@ -229,7 +234,7 @@ class _MeshNetFunction(torch.autograd.Function):
         ptab = _param_table(fc_w, fc_b, cl_w, cl_b, bn_w, bn_b)
         gtab = _param_table(g_fc_w, g_fc_b, g_cl_w, g_cl_b, g_bn_w, g_bn_b)
         B = x.shape[0]
-        dy = dy.contiguous()
+        dy = dy.contiguous().float()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         sc_bytes = lib.p2m_meshnet_backward_scratch_bytes(h, B)
         scratch = torch.empty(sc_bytes, device=dev, dtype=torch.uint8)
@@ -318,6 +323,9 @@ class Pose2Mesh(nn.Module):
         for p in params:
             if p.device != x.device:
                 raise RuntimeError("parameters and input live on different devices")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("pose2mesh_release_b200.Pose2Mesh needs contiguous float32 parameters "
+                                   f"(got {p.dtype}); the library reads them through raw device pointers")
         return _MeshNetFunction.apply(x, self._hier, self.training, self._bn_buffers(), n, *params)
 
     @torch.no_grad()
@@ -335,12 +343,7 @@ class Pose2Mesh(nn.Module):
         x = x.contiguous().float()
         dev = x.device
         h = self._hier.handle(dev.index)
-        key = (dev.index, int(n_vertex))
-        if getattr(self, "_gather_key", None) != key:
-            idx = np.ascontiguousarray(np.asarray(perm_reverse)[:n_vertex], dtype=np.int32)
-            _lib.check(lib.p2m_model_set_output_gather(h, idx.ctypes.data_as(_lib.c_int32_p), int(n_vertex)),
-                       "p2m_model_set_output_gather")
-            self._gather_key = key
+        self._set_gather(dev, perm_reverse, int(n_vertex))
         B = x.shape[0]
         y = torch.empty((B, int(n_vertex), self.num_mesh_output_chan), device=dev, dtype=torch.float32)
         ws_bytes = lib.p2m_meshnet_workspace_bytes(h, B, 0)
@@ -358,18 +361,36 @@ class Pose2Mesh(nn.Module):
                        "p2m_meshnet_forward_vertices")
         return y
 
-    def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
-        """Inference with HOST tensors through p2m_meshnet_forward_host: H2D of the poses, the eval
-        forward, D2H of the mesh, synchronised.  Used by bench.py's end-to-end figure."""
+    def _set_gather(self, dev, perm_reverse, n_vertex):
+        idx = np.ascontiguousarray(np.asarray(perm_reverse)[:n_vertex], dtype=np.int32)
+        cache = self.__dict__.setdefault("_gather_maps", {})   # device -> index list currently set on that handle
+        have = cache.get(dev.index)
+        if have is None or have.shape != idx.shape or not np.array_equal(have, idx):
+            _lib.check(_lib.load().p2m_model_set_output_gather(self._hier.handle(dev.index),
+                                                               idx.ctypes.data_as(_lib.c_int32_p), int(n_vertex)),
+                       "p2m_model_set_output_gather")
+            cache[dev.index] = idx
+
+    def forward_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None, device=None,
+                     perm_reverse=None, n_vertex: Optional[int] = None) -> torch.Tensor:
+        """Inference with HOST tensors through p2m_meshnet_forward_host: H2D of the poses, the eval forward, D2H of
+        the meshes, synchronised.  With ``perm_reverse`` / ``n_vertex`` the callers' gather
+        ``pred[:, perm_reverse[:n_vertex]]`` (lib/core/base.py:130,201) is fused into the head layer and only the
+        ``[B, n_vertex, 3]`` vertices travel back (p2m_meshnet_forward_vertices_host).  bench.py's end-to-end figure."""
         lib = _lib.load()
         dev = self.fc.weight.device if device is None else torch.device(device)
         h = self._hier.handle(dev.index)
         n_joint = self.graph_L[-1].shape[0]
         x_host = x_host.reshape(-1, n_joint, self.num_joint_input_chan).contiguous().float()
         B = x_host.shape[0]
+        gathered = perm_reverse is not None
+        rows = int(n_vertex) if gathered else self.num_vertices
+        if gathered:
+            self._set_gather(dev, perm_reverse, rows)
         if out is None:
-            out = torch.empty((B, self.num_vertices, self.num_mesh_output_chan), dtype=torch.float32,
-                              pin_memory=True)
+            out = torch.empty((B, rows, self.num_mesh_output_chan), dtype=torch.float32, pin_memory=True)
+        if tuple(out.shape) != (B, rows, self.num_mesh_output_chan) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"forward_host: `out` must be a contiguous float32 [{B}, {rows}, {self.num_mesh_output_chan}]")
         need = lib.p2m_meshnet_workspace_bytes(h, B, 0) + lib.p2m_meshnet_host_io_bytes(h, B)
         ws = getattr(self, "_host_ws", None)
         if ws is None or ws.numel() < need or ws.device != dev:
@@ -382,9 +403,10 @@ class Pose2Mesh(nn.Module):
                              list(params[2 + 2 * n:2 + 2 * n + n_bn]) + [None],
                              list(params[2 + 2 * n + n_bn:]) + [None], rm, rv, nbt)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        fn = lib.p2m_meshnet_forward_vertices_host if gathered else lib.p2m_meshnet_forward_host
         with torch.cuda.device(dev):
-            _lib.check(lib.p2m_meshnet_forward_host(h, C.byref(table), x_host.data_ptr(), out.data_ptr(), B,
-                                                    ws.data_ptr(), ws.numel(), stream), "p2m_meshnet_forward_host")
+            _lib.check(fn(h, C.byref(table), x_host.data_ptr(), out.data_ptr(), B, ws.data_ptr(), ws.numel(), stream),
+                       "p2m_meshnet_forward_host")
         return out
 
     # the reference exposes these helpers; keep them for callers that poke at them

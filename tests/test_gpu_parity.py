@@ -101,8 +101,11 @@ def test_meshnet_train_step_matches_reference_golden(name, precision):
     assert ok, ("dx", info)
     for k, p in model.named_parameters():
         got, ref = tensor_digest(p.grad), z["grad/" + k]
-        assert abs(got[1] - ref[1]) <= 1e-2 * ref[1] + 1e-6, (k, got[1], ref[1])
-        assert abs(got[2] - ref[2]) <= 2e-2 * ref[2] + 1e-12, (k, got[2], ref[2])
+        # digests of the reference's gradients per tensor: sum |g| within 2e-3 and sum g^2 within 4e-3 (the squared
+        # norm moves by twice the relative error; the ReLUs are live here, see grad_close).  Conv biases in front of
+        # a BatchNorm have a mathematically zero gradient: absolute floor.
+        assert abs(got[1] - ref[1]) <= 2e-3 * ref[1] + 1e-6, (k, got[1], ref[1])
+        assert abs(got[2] - ref[2]) <= 4e-3 * ref[2] + 1e-12, (k, got[2], ref[2])
     for k, v in model.state_dict().items():
         if "running" in k:
             np.testing.assert_allclose(v.cpu().numpy(), z["after/" + k], rtol=1e-4, atol=1e-6, err_msg=k)
@@ -157,27 +160,33 @@ def test_every_parameter_gradient_matches_oracle(precision):
 def test_layerwise_cheb_conv_matches_reference_golden(precision):
     """graph_conv_cheby drop-in against the reference's own outputs (cheb_conv.npz): odd widths
     (Fin=20, Fout=12) exercise the generic path."""
+    from pose2mesh_release_b200 import cheby_graph_conv as cgc
     from pose2mesh_release_b200.cheby_graph_conv import graph_conv_cheby
 
-    z = load_npz("cheb_conv.npz")
-    mats, _ = graph_from_fixture("smpl_small")
-    L = mats[int(z["level"])]
-    x = torch.from_numpy(z["x"]).to(dev())
-    fout, fin3 = z["weight"].shape
-    cl = torch.nn.Linear(fin3, fout).to(dev())
-    cl.weight.data.copy_(torch.from_numpy(z["weight"]))
-    cl.bias.data.copy_(torch.from_numpy(z["bias"]))
-    y = graph_conv_cheby(x, cl, None, L, fout, 3)
-    assert rel_err(y, torch.from_numpy(z["y_plain"])) < 1e-5
-    bn = torch.nn.BatchNorm1d(fout).to(dev())
-    bn.weight.data.copy_(torch.from_numpy(z["bn_weight"]))
-    bn.bias.data.copy_(torch.from_numpy(z["bn_bias"]))
-    bn.train()
-    y = graph_conv_cheby(x, cl, bn, L, fout, 3)
-    assert rel_err(y, torch.from_numpy(z["y_bn_train"])) < 1e-5
-    bn.eval()
-    y = graph_conv_cheby(x, cl, bn, L, fout, 3)
-    assert rel_err(y, torch.from_numpy(z["y_bn_eval"])) < 1e-5
+    cgc.set_default_precision(precision)
+    try:
+
+        z = load_npz("cheb_conv.npz")
+        mats, _ = graph_from_fixture("smpl_small")
+        L = mats[int(z["level"])]
+        x = torch.from_numpy(z["x"]).to(dev())
+        fout, fin3 = z["weight"].shape
+        cl = torch.nn.Linear(fin3, fout).to(dev())
+        cl.weight.data.copy_(torch.from_numpy(z["weight"]))
+        cl.bias.data.copy_(torch.from_numpy(z["bias"]))
+        y = graph_conv_cheby(x, cl, None, L, fout, 3)
+        assert rel_err(y, torch.from_numpy(z["y_plain"])) < 1e-5
+        bn = torch.nn.BatchNorm1d(fout).to(dev())
+        bn.weight.data.copy_(torch.from_numpy(z["bn_weight"]))
+        bn.bias.data.copy_(torch.from_numpy(z["bn_bias"]))
+        bn.train()
+        y = graph_conv_cheby(x, cl, bn, L, fout, 3)
+        assert rel_err(y, torch.from_numpy(z["y_bn_train"])) < 1e-5
+        bn.eval()
+        y = graph_conv_cheby(x, cl, bn, L, fout, 3)
+        assert rel_err(y, torch.from_numpy(z["y_bn_eval"])) < 1e-5
+    finally:
+        cgc.set_default_precision("fp32")
 
 
 def test_cheb_conv_functional_gradients_match_oracle():
@@ -236,7 +245,11 @@ def test_full_size_smpl_eval_against_oracle(precision):
     assert torch.isfinite(y).all()
     assert per_mesh_rel_err(y_split, y) < 1e-6
     laps = mo.laplacians_to_torch(graph_L)
-    pick = [0, 131, 255]
+    # 32 meshes against the oracle: batch ends, rows around the points where the persistent kernels' tile -> CTA
+    # assignment wraps (96 tiles per mesh over 148 CTAs), and a regular spread
+    pick = sorted({0, 1, 2, 3, 36, 37, 73, 74, 110, 111, 127, 128, 131, 147, 148, 149, 184, 185, 221, 222, 254, 255}
+                  | set(range(9, 256, 25)) | {200})
+    assert len(pick) >= 32
     with torch.no_grad():
         yo = mo.forward(sd, laps, x[pick], training=False)
     assert per_mesh_rel_err(y[pick], yo) < TOL_Y

@@ -156,3 +156,24 @@ def test_padding_vertices_are_isolated_and_reduce_to_a_dense_map(name):
         assert rel_err(y[:, iso], y_iso) < 1e-5
     if name == "smpl_like":
         assert 0.40 < frac[0] < 0.48  # 5398 of 12288 rows at the finest SMPL-size level
+
+
+def test_demo_oracle_matches_reference_golden():
+    """demo/run.py:150-158 normalisation, PoseNet (lib/models/posenet.py) and the FlatPose2Mesh concat
+    (pose2mesh_net.py:18-19), restated in oracle/demo_oracle.py, against the outputs of the unmodified reference
+    functions (tests/golden/demo_pipeline.npz, made by tests/golden/make_golden_demo.py)."""
+    from oracle import demo_oracle as do
+
+    z = load_npz("demo_pipeline.npz")
+    assert np.array_equal(z["joint_input"], load_npz("demo_input.npz")["joint_input"])
+    bbox2 = do.process_bbox(do.get_bbox(z["joint_input"]).copy())
+    np.testing.assert_allclose(bbox2, z["bbox2"], rtol=1e-7)
+    np.testing.assert_allclose(do.normalize_pose2d(z["joint_input"]), z["joint_img"][0], atol=1e-6)
+    torch.manual_seed(123)
+    sd = do.posenet_init_state_dict(17)
+    mo.randomize_bn_({("bn." + k): v for k, v in sd.items() if "batch_norm" in k}, seed=11)
+    with torch.no_grad():
+        pose3d = do.posenet_forward(sd, torch.from_numpy(z["pose2d"]).reshape(8, -1))
+    np.testing.assert_allclose(pose3d.numpy(), z["pose3d"], rtol=1e-5, atol=1e-6)
+    comb = do.flat_pose2mesh_input(torch.from_numpy(z["pose2d"]), pose3d)
+    np.testing.assert_allclose(comb.numpy(), z["pose_combine"], rtol=1e-5, atol=1e-7)

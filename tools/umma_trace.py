@@ -18,10 +18,11 @@ lib = _lib.load()
 buf = torch.zeros(8 * 512, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     cgc.graph_conv_cheby(x, cl, None, L, fout, 3)   # warm-up
-    lib.p2m_debug_set_trace(buf.data_ptr())
+    h = cgc.graph_handle(L).handle(0)
+    _lib.check(lib.p2m_debug_set_trace(h, buf.data_ptr()), "set_trace (needs a P2M_TRACE=1 build)")
     cgc.graph_conv_cheby(x, cl, None, L, fout, 3)
     torch.cuda.synchronize()
-    lib.p2m_debug_set_trace(None)
+    lib.p2m_debug_set_trace(h, None)
 t = buf.cpu().numpy().reshape(8, 512)
 names = {0: "producer", 1: "bload", 2: "mma", 3: "epilogue"}
 ev_all = []
