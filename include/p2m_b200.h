@@ -104,6 +104,15 @@ int p2m_debug_set_fuse_head(p2m_model_t* m, int enable);
  * connected rows through the conv on index-list tiles.  Same results up to fp32 association.  1 (default) = on levels
  * where at least 40 % of the rows are isolated, 2 = wherever the tile families exist, 0 = off.                       */
 int p2m_debug_set_elide_padding(p2m_model_t* m, int enable);
+/* Eval mode, on the elided levels: both children of a fake vertex are fake and carry identical values, so only one
+ * representative per class of identical isolated rows is computed and the output rows of the others are filled from
+ * it at the end; p2m_meshnet_forward_vertices (which returns connected rows only) computes no isolated row at all.
+ * 1 (default) = on, 0 = every isolated row is computed.  Training always computes every row (BatchNorm statistics). */
+int p2m_debug_set_dedup_padding(p2m_model_t* m, int enable);
+/* Backward, tensor-core layers: 1 (default) = the weight gradient is formed from the Chebyshev basis of the GRADIENT
+ * (sum_rows dz (x) T_k(x) = sum_rows T_k(dz) (x) x, L~ symmetric), re-using the L~dz the backward-data pass computes;
+ * 0 = from the basis of the layer input, rebuilt on chip with its 2-hop halo.  Same result up to fp32 association. */
+int p2m_debug_set_dw_swap(p2m_model_t* m, int enable);
 
 /* Bytes of device workspace p2m_meshnet_forward needs for batch B.  In training mode the workspace
  * also carries what p2m_meshnet_backward reads, so it must stay alive and untouched in between.   */
@@ -181,6 +190,53 @@ typedef struct {
 } p2m_conv_bwd_args_t;
 int p2m_cheb_conv_bwd(p2m_model_t* m, const p2m_conv_bwd_args_t* a, void* workspace, size_t workspace_bytes,
                       p2m_stream_t stream);
+
+/* ---- the step in front of MeshNet --------------------------------------------
+ * FlatPose2Mesh.forward (lib/models/pose2mesh_net.py:16-22) in eval mode: PoseNet, the 2-D -> 3-D pose lifter
+ * (lib/models/posenet.py:41-87: Linear(2J,H), `num_stage` residual stages of BN-ReLU-Linear(H,H)-BN-ReLU-Linear(H,H),
+ * Linear(H,3J); running-stat BatchNorm, dropout off), and pose_combine = cat(pose2d, pose3d / 1000) [B, J, 5],
+ * MeshNet's input.  All pointers are device pointers with the reference's state_dict shapes.               */
+typedef struct {
+  const float* w1_w; const float* w1_b;                                     /* [H, H], [H]   */
+  const float* w2_w; const float* w2_b;
+  const float* bn1_w; const float* bn1_b; const float* bn1_rm; const float* bn1_rv;   /* [H] each */
+  const float* bn2_w; const float* bn2_b; const float* bn2_rm; const float* bn2_rv;
+} p2m_posenet_stage_t;
+typedef struct {
+  int32_t num_joint, hidden, num_stage;
+  const float* w1_w; const float* w1_b;        /* [H, 2J], [H]  */
+  const float* w2_w; const float* w2_b;        /* [3J, H], [3J] */
+  const p2m_posenet_stage_t* stages;           /* [num_stage] (host array of device pointers) */
+} p2m_posenet_params_t;
+size_t p2m_posenet_workspace_bytes(int batch, int hidden);
+/* pose2d [B, 2J] -> pose3d [B, 3J]; pose_combine (optional) [B, J, 5].  Enqueued on `stream` of the current device. */
+int p2m_posenet_forward(const p2m_posenet_params_t* params, const float* pose2d, float* pose3d, float* pose_combine,
+                        int batch, void* workspace, size_t workspace_bytes, p2m_stream_t stream);
+
+/* ---- the steps either side of the model in the reference's callers ----------
+ * Joint regression (lib/core/base.py:131,204; demo/run.py:171): joints [B, n_joint, C] = joint_regressor
+ * [n_joint, n_vertex] @ vertices [B, n_vertex, C] (C <= 4), on the gathered vertices of
+ * p2m_meshnet_forward_vertices.                                                                        */
+int p2m_regress_joints(const float* joint_regressor, const float* vertices, float* joints, int batch, int n_joint,
+                       int n_vertex, int chans, p2m_stream_t stream);
+/* The demo's input normalisation (demo/run.py:150-158): joints_px [B, J, 2] in image pixels -> pose2d [B, J, 2],
+ * zero mean / unit std per pose and coordinate in the aspect-preserving box of the (input_h, input_w) network input
+ * (cfg.MODEL.input_shape = (384, 288)).  truncate_like_int_input = 1 reproduces the reference on INTEGER joint
+ * arrays (demo/h36m_joint_input.npy is int64: the transformed coordinates are truncated when written back). */
+int p2m_normalize_pose2d(const float* joints_px, float* pose2d, int batch, int n_joint, int input_h, int input_w,
+                         int truncate_like_int_input, p2m_stream_t stream);
+
+/* ---- the mesh losses (lib/core/loss.py:10-23,62-114) ---------------------------
+ * One pass over (mesh, face): sums[0] = sum of the NormalVectorLoss terms, sums[1] = sum of the EdgeLengthLoss terms
+ * over (B, 3 n_face) (fp64, device; the losses are sums / (3 B n_face)).  If grad_out [B, n_vertex, 3] is given it
+ * receives  grad_scale[0] * d sums[0] / d coord_out + grad_scale[1] * d sums[1] / d coord_out  (grad_scale: device
+ * float[2], i.e. upstream gradient / (3 B n_face)).  faces: device int32 [n_face, 3].                    */
+int p2m_mesh_losses(const float* coord_out, const float* coord_gt, const int32_t* faces, int batch, int n_vertex,
+                    int n_face, const float* grad_scale, double* sums, float* grad_out, p2m_stream_t stream);
+/* CoordLoss: *sum = sum |pred * valid - target * valid| over n elements (valid may be NULL = ones, else same shape);
+ * grad_out (optional, n floats) = grad_scale[0] * sign(.) * valid.                                        */
+int p2m_coord_loss(const float* pred, const float* target, const float* valid, int64_t n, const float* grad_scale,
+                   double* sum, float* grad_out, p2m_stream_t stream);
 
 /* ---- host-side graph baking helper (CPU; no device work) -------------------------------------------
  * One level of the reference's greedy heavy-edge matching (lib/coarsening.py:153-211, HEM_one_level),

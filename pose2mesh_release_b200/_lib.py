@@ -82,11 +82,22 @@ class ConvBwdArgs(C.Structure):
     ]
 
 
+class PoseNetStage(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1_w", "w1_b", "w2_w", "w2_b", "bn1_w", "bn1_b", "bn1_rm", "bn1_rv",
+                                          "bn2_w", "bn2_b", "bn2_rm", "bn2_rv")]
+
+
+class PoseNetParams(C.Structure):
+    _fields_ = [("num_joint", C.c_int32), ("hidden", C.c_int32), ("num_stage", C.c_int32),
+                ("w1_w", C.c_void_p), ("w1_b", C.c_void_p), ("w2_w", C.c_void_p), ("w2_b", C.c_void_p),
+                ("stages", C.POINTER(PoseNetStage))]
+
+
 EXPORTS = [
     "p2m_model_create", "p2m_model_destroy", "p2m_model_num_layers", "p2m_model_layer_info",
-    "p2m_model_set_precision", "p2m_debug_kernel_status", "p2m_debug_set_trace", "p2m_debug_set_split_t1", "p2m_debug_set_fuse_head", "p2m_debug_set_elide_padding", "p2m_model_set_profiling", "p2m_model_layer_times_ms", "p2m_meshnet_workspace_bytes", "p2m_meshnet_backward_scratch_bytes",
+    "p2m_model_set_precision", "p2m_debug_kernel_status", "p2m_debug_set_trace", "p2m_debug_set_split_t1", "p2m_debug_set_fuse_head", "p2m_debug_set_elide_padding", "p2m_debug_set_dedup_padding", "p2m_debug_set_dw_swap", "p2m_model_set_profiling", "p2m_model_layer_times_ms", "p2m_meshnet_workspace_bytes", "p2m_meshnet_backward_scratch_bytes",
     "p2m_meshnet_forward", "p2m_meshnet_backward", "p2m_model_set_output_gather", "p2m_meshnet_forward_vertices", "p2m_meshnet_host_io_bytes", "p2m_meshnet_forward_host", "p2m_meshnet_forward_vertices_host",
-    "p2m_cheb_conv_workspace_bytes", "p2m_cheb_conv_fwd", "p2m_cheb_conv_bwd", "p2m_graph_match_level",
+    "p2m_cheb_conv_workspace_bytes", "p2m_cheb_conv_fwd", "p2m_cheb_conv_bwd", "p2m_graph_match_level", "p2m_posenet_workspace_bytes", "p2m_posenet_forward", "p2m_regress_joints", "p2m_normalize_pose2d", "p2m_mesh_losses", "p2m_coord_loss",
     "p2m_last_error", "p2m_version", "p2m_launch_count", "p2m_launch_count_reset",
 ]
 
@@ -128,6 +139,10 @@ def load() -> C.CDLL:
         lib.p2m_debug_set_fuse_head.restype = C.c_int
         lib.p2m_debug_set_elide_padding.argtypes = [vp, C.c_int]
         lib.p2m_debug_set_elide_padding.restype = C.c_int
+        lib.p2m_debug_set_dedup_padding.argtypes = [vp, C.c_int]
+        lib.p2m_debug_set_dedup_padding.restype = C.c_int
+        lib.p2m_debug_set_dw_swap.argtypes = [vp, C.c_int]
+        lib.p2m_debug_set_dw_swap.restype = C.c_int
         lib.p2m_debug_set_trace.argtypes = [vp, vp]
         lib.p2m_debug_set_trace.restype = C.c_int
         lib.p2m_debug_kernel_status.argtypes = [vp, c_int32_p]
@@ -157,6 +172,18 @@ def load() -> C.CDLL:
         lib.p2m_cheb_conv_fwd.restype = C.c_int
         lib.p2m_cheb_conv_bwd.argtypes = [vp, C.POINTER(ConvBwdArgs), vp, sz, vp]
         lib.p2m_cheb_conv_bwd.restype = C.c_int
+        lib.p2m_posenet_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        lib.p2m_posenet_workspace_bytes.restype = sz
+        lib.p2m_posenet_forward.argtypes = [C.POINTER(PoseNetParams), vp, vp, vp, C.c_int, vp, sz, vp]
+        lib.p2m_posenet_forward.restype = C.c_int
+        lib.p2m_regress_joints.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        lib.p2m_regress_joints.restype = C.c_int
+        lib.p2m_normalize_pose2d.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        lib.p2m_normalize_pose2d.restype = C.c_int
+        lib.p2m_mesh_losses.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.p2m_mesh_losses.restype = C.c_int
+        lib.p2m_coord_loss.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+        lib.p2m_coord_loss.restype = C.c_int
         lib.p2m_graph_match_level.argtypes = [i64, c_int32_p, c_int32_p, C.POINTER(C.c_double), c_int64_p,
                                               C.POINTER(C.c_double), c_int32_p]
         lib.p2m_graph_match_level.restype = i32

@@ -361,8 +361,12 @@ constexpr int W_PROD = 16;
 constexpr int W_XLOAD = 16, N_XLOAD = 2, W_BLOAD = 18, W_MMA = 19, W_EPI0 = 20;
 constexpr int NUM_THREADS2 = 24 * 32;
 
-template <int N, int NS, int XS>
+// RM = 1: the residual is the 2:1 channel resampling of a 2N-wide tensor (F.interpolate(linear, align_corners=False)
+// from 2N to N channels is the mean of channel pairs: src = 2j + 0.5), fetched as two 16-byte loads per four outputs
+// instead of the generic 2-tap gather; a separate instantiation so that the other layers keep their register budget.
+template <int N, int NS, int XS, int RM = 0>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid_constant__ KParams p) {
+  constexpr bool PAIR = (RM == 1);
   constexpr int B_BLOCK_BYTES = N * 128;
   constexpr int SLOT_BYTES = A_BLOCK_BYTES + B_BLOCK_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16(TILE_M, N);
@@ -604,7 +608,24 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
 #pragma unroll
           for (int i0 = 0; i0 < 32 / RPI; i0 += IB) {
             float4 rv[IB];
-            if (p.ep.res != nullptr && p.res_identity) {
+            if (PAIR) {
+#pragma unroll
+              for (int i = 0; i < IB; ++i) {
+                const int rr = (i0 + i) * RPI + prow;
+                const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+                const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
+                const int vtx = own_w[rr];
+                const long long r = mesh0 + vtx;
+                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (vtx >= 0) {
+                  const float4* src =
+                      reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + 2 * n);
+                  const float4 a = __ldg(src), b = __ldg(src + 1);
+                  rv[i] = make_float4(0.5f * a.x + 0.5f * a.y, 0.5f * a.z + 0.5f * a.w, 0.5f * b.x + 0.5f * b.y,
+                                      0.5f * b.z + 0.5f * b.w);
+                }
+              }
+            } else if (p.ep.res != nullptr && p.res_identity) {
 #pragma unroll
               for (int i = 0; i < IB; ++i) {
                 const int rr = (i0 + i) * RPI + prow;
@@ -633,7 +654,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
                   for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
                 }
                 const long long r = mesh0 + vtx;
-                if (p.ep.res != nullptr) {
+                if (PAIR) {
+                  o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
+                } else if (p.ep.res != nullptr) {
                   if (p.res_identity) {
                     o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
                   } else {
@@ -775,8 +798,15 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           uint2 hi, lo;
           split4(v, hi, lo);
           const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
-          sts_u2(a_hi, hi);
-          sts_u2(a_lo, lo);
+          // the four consecutive rows of a warp share (row & 4), i.e. the 64-byte half their hi parts go to: odd row
+          // groups store lo first, so that every store instruction of the warp covers both halves (no replays)
+          if (rg & 1) {
+            sts_u2(a_lo, lo);
+            sts_u2(a_hi, hi);
+          } else {
+            sts_u2(a_hi, hi);
+            sts_u2(a_lo, lo);
+          }
         }
         fence_async_proxy();
         __syncwarp();
@@ -814,7 +844,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         for (int ps = 0; ps < 2; ++ps) {
           const uint32_t i = ps ? row1 : row0;
           uint2 hi, lo;
-          split4(ps ? v1 : v0, hi, lo);
+          float4 v = ps ? v1 : v0;
+          if (p.a_scale != nullptr) {  // backward-data pass: gradients are scaled into fp16's range (power of two)
+            v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
+          }
+          split4(v, hi, lo);
           const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
           if (rg & 1) {
             sts_u2(a_lo, lo);
@@ -900,9 +934,17 @@ struct DwParams {
   const float* g;        // dz [rows, fout_total]
   int fout_total, m_off, m_cols;
   int chunk0, n_chunk;   // feature chunks [chunk0, chunk0 + n_chunk), n_chunk <= 2
-  const float* a_scale;  // device scalar (power of two) applied to dz before the fp16 split
+  const float* a_scale;  // device scalar (power of two) applied to the gradient tensor before the fp16 split
   float* dw;             // [fout_total, 3*fin], column = f*3 + k  (reference layout), accumulated atomically
   int* status;
+  // Swapped roles (L~ symmetric:  sum_rows dz (x) T_k(X) = sum_rows T_k(dz) (x) X): `x` is the GRADIENT dz
+  // [rows, fin := layer Fout] whose basis the producers build (scaled by a_scale), `t1` = L~ dz as left behind by
+  // the backward-data pass (launch_cheb_t1), `g` the layer INPUT [rows(/2), fout_total := layer Fin] (plain tile,
+  // unscaled, read at row >> 1 under the virtual unpool).  The accumulator rows are then input features and the
+  // columns output channels: dw[o][f*3+k] with o from the gathered side.  No 2-hop halo, no on-chip T1.
+  const float* t1;
+  int g_unpool;
+  int swap;
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
@@ -925,9 +967,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
   unsigned char* ring = smem_raw;                      // [DW_NS] T blocks
   unsigned char* gblk = ring + DW_NS * A_BLOCK_BYTES;  // dz tile blocks: hi g0, hi g1, lo g0, lo g1
   float* Xs = reinterpret_cast<float*>(gblk + DW_G_BYTES);
-  const size_t xs_stage_floats = (size_t)p.max_h2 * FC;
-  float* T1s = Xs + XS * xs_stage_floats;
-  unsigned char* meta_s = reinterpret_cast<unsigned char*>(T1s + (size_t)p.max_h1 * FC);
+  const bool t1g = (p.t1 != nullptr);
+  const size_t xs_stage_floats = (size_t)(t1g ? TILE_M : p.max_h2) * FC;
+  float* T1s = Xs + XS * xs_stage_floats;                   // [XS | 1][max_h1][32]
+  const size_t t1_stage_floats = (size_t)p.max_h1 * FC;
+  unsigned char* meta_s = reinterpret_cast<unsigned char*>(T1s + (t1g ? XS : 1) * t1_stage_floats);
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta_s + 2 * (size_t)p.meta_stride);
   uint64_t* b_t_full = bars;                 // [DW_NS]
   uint64_t* b_t_empty = b_t_full + DW_NS;    // [DW_NS]
@@ -995,7 +1039,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
       mbar_wait_relaxed(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 22);
       const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
       const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
-      const int h2 = hdr->h2;
+      const int h2 = t1g ? TILE_M : hdr->h2;  // T1 given: only the tile's own rows of x are staged ...
+      const int h1 = hdr->h1;
       const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);
       const long long mesh_row0 = (long long)b * p.V;
       for (int c = 0; c < n_chunk; ++c, ++g) {
@@ -1011,6 +1056,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
             cp_async16(dst0 + i * 128, src0 + r * p.fin);
           } else {
             sts_f4(dst0 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+        if (t1g) {  // ... plus the T1 rows of the tile and its 1-hop halo
+          const uint32_t dst1 = smem_u32(T1s + xs * t1_stage_floats) + q * 16;
+          const float* src1 = p.t1 + (p.chunk0 + c) * FC + q * 4;
+          for (int i = rg; i < h1; i += 8) {
+            const int v = halo[i];
+            if (v >= 0)
+              cp_async16(dst1 + i * 128, src1 + (mesh_row0 + v) * p.fin);
+            else
+              sts_f4(dst1 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
           }
         }
         cp_async_arrive_noinc(smem_u32(b_x_full + xs));
@@ -1060,8 +1116,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int f = (p.chunk0 + c) * FC + j;
-          atomicAdd(drow + f * 3 + k, (__uint_as_float(hi[j]) + __uint_as_float(lo[j])) * inv);
+          const int f = (p.chunk0 + c) * FC + j;  // channel of the gathered side
+          const float v = (__uint_as_float(hi[j]) + __uint_as_float(lo[j])) * inv;
+          if (p.swap)  // accumulator row = input feature (plain side), column = output channel
+            atomicAdd(p.dw + (size_t)f * 3 * p.fout_total + (size_t)(p.m_off + o_local) * 3 + k, v);
+          else
+            atomicAdd(drow + f * 3 + k, v);
         }
       }
     }
@@ -1084,7 +1144,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
         const uint32_t mb_a = smem_u32(mb);
         const uint32_t rp_a = mb_a + hdr->off_rp, ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
         ent_a = mb_a + hdr->off_ent;
-        const int h1 = hdr->h1;
+        const int h1 = t1g ? 0 : hdr->h1;  // the trimmed metadata has no T1 row order
 #pragma unroll
         for (int t = 0; t < T1_ROWS; ++t) {
           const int j = rg + 64 * t;
@@ -1100,7 +1160,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
         r0e = lds_u16(rp_a + 2 * row0) | (lds_u16(rp_a + 2 * row0 + 2) << 16);
         r1e = lds_u16(rp_a + 2 * row1) | (lds_u16(rp_a + 2 * row1 + 2) << 16);
       }
-      // dz tile -> (hi, lo) fp16 blocks, MN-major [row][channel]
+      // plain-side tile (dz, or the layer input in swapped mode) -> (hi, lo) fp16 blocks, MN-major [row][channel]
       mbar_wait(smem_u32(b_g_empty), (it & 1) ^ 1, abort_flag, p.status, 28);
       {
         const int n_rows = min(TILE_M, p.V - pat * TILE_M);
@@ -1112,9 +1172,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
           for (int jj = 0; jj < 4; ++jj) {
             const int col = q * 4 + 32 * jj;  // channel inside this launch's 128-channel slice
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < n_rows && col < p.m_cols)
-              v = *reinterpret_cast<const float4*>(p.g + (r_base + i) * p.fout_total + p.m_off + col);
-            v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
+            if (i < n_rows && col < p.m_cols) {
+              const long long rr = p.g_unpool ? ((r_base + i) >> 1) : (r_base + i);
+              v = *reinterpret_cast<const float4*>(p.g + rr * p.fout_total + p.m_off + col);
+            }
+            if (!p.swap) {  // legacy roles: this side is the gradient
+              v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
+            }
             uint2 hi, lo;
             split4(v, hi, lo);
             const uint32_t off = (uint32_t)(col >> 6) * A_BLOCK_BYTES + sw128_off(i, (col & 63) >> 3) + ((col >> 2) & 1) * 8;
@@ -1130,13 +1194,15 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
         const int xs = gcnt % XS;
         mbar_wait(smem_u32(b_x_full + xs), (gcnt / XS) & 1, abort_flag, p.status, 29);
         const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
-        const uint32_t t1s_q = t1s_a + q * 16;
+        const uint32_t t1s_q = t1s_a + (t1g ? (uint32_t)(xs * t1_stage_floats * 4) : 0u) + q * 16;
+        if (!t1g) {
 #pragma unroll
-        for (int t = 0; t < T1_ROWS; ++t) {
-          if (t1_row[t] != 0xFFFFu)
-            sts_f4(t1s_q + t1_row[t] * 128, gather_row4(ent_a, t1_e[t] & 0xFFFFu, t1_e[t] >> 16, xs_q));
+          for (int t = 0; t < T1_ROWS; ++t) {
+            if (t1_row[t] != 0xFFFFu)
+              sts_f4(t1s_q + t1_row[t] * 128, gather_row4(ent_a, t1_e[t] & 0xFFFFu, t1_e[t] >> 16, xs_q));
+          }
+          producer_barrier();
         }
-        producer_barrier();
         float4 tv[3][2];
         {
           const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
@@ -1148,6 +1214,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
           const float4 a = tv[0][0], c2 = tv[0][1];
           tv[2][0] = make_float4(2.f * g0.x - a.x, 2.f * g0.y - a.y, 2.f * g0.z - a.z, 2.f * g0.w - a.w);
           tv[2][1] = make_float4(2.f * g1.x - c2.x, 2.f * g1.y - c2.y, 2.f * g1.z - c2.z, 2.f * g1.w - c2.w);
+          if (p.swap) {  // the gathered side is the gradient: into fp16's range before the split
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+              for (int ps = 0; ps < 2; ++ps) {
+                tv[k][ps].x *= a_scale; tv[k][ps].y *= a_scale; tv[k][ps].z *= a_scale; tv[k][ps].w *= a_scale;
+              }
+          }
         }
         const uint32_t u0 = ucnt;
 #pragma unroll
@@ -1356,12 +1430,12 @@ bool make_row_tmap(CUtensorMap* tm, const float* base, long long rows, int fin, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int N, int NS, int XS>
+template <int N, int NS, int XS, int RM = 0>
 int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   const DevLevel& g = *a.g;
   const int mode = a.plain ? 2 : (a.t1 != nullptr ? 1 : 0);
   const size_t smem = smem_bytes_args(N, NS, XS, a);
-  auto kern = k_cheb_conv_umma<N, NS, XS>;
+  auto kern = k_cheb_conv_umma<N, NS, XS, RM>;
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KParams p;
   p.x = a.x;
@@ -1417,6 +1491,9 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
 template <int N>
 int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   constexpr int NS = (N == 256) ? 2 : 3;
+  if (N == 128 && a.ep.res != nullptr && a.ep.res_F == 2 * N && (a.t1 != nullptr || a.plain) && a.head_z == nullptr &&
+      smem_bytes_args(N, NS, 2, a) <= SMEM_LIMIT)
+    return launch_cfg<N, NS, 2, (N == 128 ? 1 : 0)>(a, status, zero_row, sm_count, s);  // pair-mean residual (256 -> 128)
   if (a.t1 != nullptr || a.plain) {
     if (smem_bytes_args(N, NS, 2, a) <= SMEM_LIMIT) return launch_cfg<N, NS, 2>(a, status, zero_row, sm_count, s);
     if (smem_bytes_args(N, NS, 1, a) > SMEM_LIMIT) {
@@ -1435,6 +1512,25 @@ int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_c
 // host side
 // =====================================================================================
 namespace {
+// The producers store a tile row's fp16 hi part into one 64-byte half of its 128-byte A-block row and the lo part
+// into the other; which half is which follows the row's swizzle bit (row & 4).  A warp stores four rows per
+// instruction (row groups 4w .. 4w+3 of the order below, odd groups lo first), so an instruction is free of bank
+// replays iff positions (0, 2) of an aligned group of four hold rows of different half classes, and so do (1, 3).
+// Re-deal a length-sorted order accordingly: two rows of each class per group, taken in sorted order (a group's rows
+// still have similar lengths).  Pure re-ordering of which thread produces which row: results are unchanged.
+void balance_store_halves(std::vector<unsigned short>* ord) {
+  std::vector<unsigned short> q0, q1;
+  for (unsigned short r : *ord) ((r & 4) ? q1 : q0).push_back(r);
+  if (q0.size() != q1.size() || (q0.size() & 1)) return;
+  size_t o = 0;
+  for (size_t g = 0; g + 1 < q0.size(); g += 2) {
+    (*ord)[o++] = q0[g];
+    (*ord)[o++] = q0[g + 1];
+    (*ord)[o++] = q1[g];
+    (*ord)[o++] = q1[g + 1];
+  }
+}
+
 // Trimmed blob of one tile whose 128 own rows are given by an index list (-1 = empty slot): own rows, their 1-hop
 // halo, the CSR of the own rows with staged-row slots as columns, the own rows in length-sorted order.
 bool make_indexed_blob(const std::vector<int>& own, const int* rowptr, const int* colidx, const float* val,
@@ -1478,6 +1574,7 @@ bool make_indexed_blob(const std::vector<int>& own, const int* rowptr, const int
   std::stable_sort(ord2.begin(), ord2.end(), [&](unsigned short a, unsigned short b2) {
     return (int)rp[a + 1] - (int)rp[a] > (int)rp[b2 + 1] - (int)rp[b2];
   });
+  balance_store_halves(&ord2);
   TileHeader t{};
   t.n_rows = n_rows;
   t.h1 = h1;
@@ -1539,6 +1636,11 @@ int build_tileset(const std::vector<int>& rows, const int* rowptr, const int* co
 }
 }  // namespace
 
+int build_index_tiles(const std::vector<int>& rows, const int* rowptr, const int* colidx, const float* val, int V,
+                      TileSet* ts, std::vector<void*>* owned) {
+  return build_tileset(rows, rowptr, colidx, val, V, ts, owned);
+}
+
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
                           std::vector<void*>* owned) {
   const int P = (V + TILE_M - 1) / TILE_M;
@@ -1598,6 +1700,7 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
     for (int i = 0; i < TILE_M; ++i) ord2[i] = (unsigned short)i;
     std::stable_sort(ord1.begin(), ord1.end(), [&](unsigned short a, unsigned short b2) { return row_len(a) > row_len(b2); });
     std::stable_sort(ord2.begin(), ord2.end(), [&](unsigned short a, unsigned short b2) { return row_len(a) > row_len(b2); });
+    balance_store_halves(&ord2);
     TileHeader h{};
     h.n_rows = n_rows;
     h.h1 = h1;
@@ -1720,9 +1823,11 @@ int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val
 }
 
 
-size_t dw_smem_bytes(int XS, const DevLevel& g) {
-  return 1024 + (size_t)DW_NS * A_BLOCK_BYTES + DW_G_BYTES + (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4 +
-         2 * (size_t)g.meta_stride + 8 * (2 * DW_NS + 2 * XS + 8) + 32;
+size_t dw_smem_bytes(int XS, const DevLevel& g, bool t1_given = false) {
+  const size_t stage = t1_given ? (size_t)XS * (TILE_M + g.max_h1) * FC * 4
+                                : (size_t)XS * g.max_h2 * FC * 4 + (size_t)g.max_h1 * FC * 4;
+  return 1024 + (size_t)DW_NS * A_BLOCK_BYTES + DW_G_BYTES + stage + 2 * (size_t)(t1_given ? g.meta1_stride : g.meta_stride) +
+         8 * (2 * DW_NS + 2 * XS + 8) + 32;
 }
 
 bool umma_dw_supported(const DevLevel& g, int fin, int fout) {
@@ -1732,16 +1837,39 @@ bool umma_dw_supported(const DevLevel& g, int fin, int fout) {
   return dw_smem_bytes(1, g) <= SMEM_LIMIT;
 }
 
+namespace {
+int launch_dw_kernels(const DevLevel& g, DwParams p, int gathered_width, int plain_width, bool t1_given, int sm_count,
+                      cudaStream_t s) {
+  const int xs = dw_smem_bytes(2, g, t1_given) <= SMEM_LIMIT ? 2 : 1;
+  const size_t smem = dw_smem_bytes(xs, g, t1_given);
+  if (smem > SMEM_LIMIT) {
+    set_error("umma_dw: does not fit shared memory");
+    return P2M_ERR_INVALID;
+  }
+  auto kern = (xs == 2) ? k_cheb_dw_umma<2> : k_cheb_dw_umma<1>;
+  P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(p.n_tiles, sm_count);
+  const int total_chunks = gathered_width / FC;
+  for (int m_off = 0; m_off < plain_width; m_off += 128) {
+    p.m_off = m_off;
+    p.m_cols = std::min(128, plain_width - m_off);
+    for (int c0 = 0; c0 < total_chunks; c0 += 2) {
+      p.chunk0 = c0;
+      p.n_chunk = std::min(2, total_chunks - c0);
+      kern<<<grid, NUM_THREADS2, smem, s>>>(p);
+      P2M_LAUNCH_OK();
+    }
+  }
+  return P2M_OK;
+}
+}  // namespace
+
 int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout, const float* dz,
                    const float* a_scale, float* dw_ref, int* status, int sm_count, cudaStream_t s) {
   if (!umma_dw_supported(g, fin, fout)) {
     set_error("umma_dw: unsupported shape");
     return P2M_ERR_INVALID;
   }
-  const int xs = dw_smem_bytes(2, g) <= SMEM_LIMIT ? 2 : 1;
-  const size_t smem = dw_smem_bytes(xs, g);
-  auto kern = (xs == 2) ? k_cheb_dw_umma<2> : k_cheb_dw_umma<1>;
-  P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DwParams p;
   p.x = x;
   p.in_unpool = in_unpool;
@@ -1759,19 +1887,48 @@ int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, 
   p.a_scale = a_scale;
   p.dw = dw_ref;
   p.status = status;
-  const int grid = std::min(p.n_tiles, sm_count);
-  const int total_chunks = fin / FC;
-  for (int m_off = 0; m_off < fout; m_off += 128) {
-    p.m_off = m_off;
-    p.m_cols = std::min(128, fout - m_off);
-    for (int c0 = 0; c0 < total_chunks; c0 += 2) {
-      p.chunk0 = c0;
-      p.n_chunk = std::min(2, total_chunks - c0);
-      kern<<<grid, NUM_THREADS2, smem, s>>>(p);
-      P2M_LAUNCH_OK();
-    }
+  p.t1 = nullptr;
+  p.g_unpool = 0;
+  p.swap = 0;
+  return launch_dw_kernels(g, p, fin, fout, false, sm_count, s);
+}
+
+// dW from the basis of the GRADIENT (see DwParams::swap): dz [rows, fout], t1_dz = L~ dz for EVERY row of the level,
+// x the layer input [rows(/2), fin]
+bool umma_dw_swapped_supported(const DevLevel& g, int fin, int fout) {
+  if (g.tile_meta1 == nullptr || g.n_pattern <= 0 || g.max_h1 > 256) return false;
+  if (fout % FC != 0 || fout < FC || fout > 256) return false;       // gathered side: dz
+  if (fin != 64 && fin != 128 && fin != 256) return false;           // plain side: x
+  return dw_smem_bytes(1, g, true) <= SMEM_LIMIT;
+}
+int launch_umma_dw_swapped(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout,
+                           const float* dz, const float* t1_dz, const float* a_scale, float* dw_ref, int* status,
+                           int sm_count, cudaStream_t s) {
+  if (!umma_dw_swapped_supported(g, fin, fout) || t1_dz == nullptr) {
+    set_error("umma_dw_swapped: unsupported shape");
+    return P2M_ERR_INVALID;
   }
-  return P2M_OK;
+  DwParams p;
+  p.x = dz;
+  p.in_unpool = 0;
+  p.V = g.V;
+  p.P = g.n_pattern;
+  p.fin = fout;                 // width of the gathered tensor
+  p.n_tiles = batch * g.n_pattern;
+  p.meta = g.tile_meta1;
+  p.meta_bytes = g.tile_meta1_bytes;
+  p.meta_stride = g.meta1_stride;
+  p.max_h1 = g.max_h1;
+  p.max_h2 = g.max_h1;
+  p.g = x;
+  p.fout_total = fin;           // width of the plain tensor
+  p.a_scale = a_scale;
+  p.dw = dw_ref;
+  p.status = status;
+  p.t1 = t1_dz;
+  p.g_unpool = in_unpool;
+  p.swap = 1;
+  return launch_dw_kernels(g, p, fout, fin, true, sm_count, s);
 }
 
 int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s,
@@ -1860,6 +2017,62 @@ __global__ void __launch_bounds__(256) k_pack_iso(const float* __restrict__ W, f
 int launch_umma_pack_iso(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s) {
   const int total = (fin / FC) * fout * 8;
   k_pack_iso<<<(total + 255) / 256, 256, 0, s>>>(W, c, fin, fout, static_cast<unsigned char*>(wpack));
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// Backward-data as a forward conv (p2m_api.cu): dX = [dz | L~dz | (2L~^2 - I)dz] * W'^T with W'[f][o*3 + k] = W[o][f*3 + k]
+// (L~ symmetric).  Same K-block image as k_pack_weights for a layer with Fin' = fout, Fout' = fin.
+__global__ void __launch_bounds__(256) k_pack_weights_t(const float* __restrict__ W, int fin, int fout,
+                                                        unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int n_blocks = (fout / FC) * 3;
+  const int total = n_blocks * fin * 8;
+  if (idx >= total) return;
+  const int j = idx & 7;
+  const int n = (idx >> 3) % fin;   // output channel of the backward conv = input feature f
+  const int u = (idx >> 3) / fin;
+  const int c = u / 3, k = u % 3;
+  const int o0 = c * FC + (j & 3) * 8;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float w = W[(size_t)(o0 + e) * fin * 3 + (size_t)n * 3 + k] * W_SCALE;
+    const __half hi = __float2half_rn(w);
+    h[e] = (j < 4) ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)u * fin * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
+}
+int launch_umma_pack_weights_t(const float* W, int fin, int fout, void* wpack, cudaStream_t s) {
+  const int total = (fout / FC) * 3 * fin * 8;
+  k_pack_weights_t<<<(total + 255) / 256, 256, 0, s>>>(W, fin, fout, static_cast<unsigned char*>(wpack));
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+// ... and the combined weights of the isolated rows, transposed: B[n = f][o] = W[o][3f] + c W[o][3f+1] + (2c^2-1) W[o][3f+2]
+__global__ void __launch_bounds__(256) k_pack_iso_t(const float* __restrict__ W, float c, int fin, int fout,
+                                                    unsigned char* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = (fout / FC) * fin * 8;
+  if (idx >= total) return;
+  const int j = idx & 7;
+  const int n = (idx >> 3) % fin;
+  const int cc = (idx >> 3) / fin;
+  const int o0 = cc * FC + (j & 3) * 8;
+  const float c2 = 2.f * c * c - 1.f;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float* wr = W + (size_t)(o0 + e) * fin * 3 + (size_t)n * 3;
+    const float w = (wr[0] + c * wr[1] + c2 * wr[2]) * W_SCALE;
+    const __half hi = __float2half_rn(w);
+    h[e] = (j < 4) ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)cc * fin * 128 + sw128_off(n, j)) = *reinterpret_cast<const uint4*>(h);
+}
+int launch_umma_pack_iso_t(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s) {
+  const int total = (fout / FC) * fin * 8;
+  k_pack_iso_t<<<(total + 255) / 256, 256, 0, s>>>(W, c, fin, fout, static_cast<unsigned char*>(wpack));
   P2M_LAUNCH_OK();
   return P2M_OK;
 }

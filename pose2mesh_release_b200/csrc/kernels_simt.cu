@@ -210,6 +210,55 @@ int launch_cheb_basis_bwd(const DevLevel& g, const float* dT, int rows, int F, f
   return P2M_OK;
 }
 
+// Finishing pass of the tensor-core backward-data path (p2m_api.cu): pair-sum for the virtual unpool and the
+// transposed channel resampling of the residual gradient.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_dx_finish(const float* __restrict__ dxl, long long rows_out, int F,
+                                                   const float* __restrict__ g_res, int res_Fout,
+                                                   const int* __restrict__ t_ptr, const int* __restrict__ t_idx,
+                                                   const float* __restrict__ t_w, int pairsum, float* __restrict__ out) {
+  using vec = typename VecT<VEC>::type;
+  const int fg = F / VEC;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_out * fg) return;
+  const long long ro = idx / fg;
+  const int f = (int)(idx - ro * fg);
+  float total[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) total[e] = 0.f;
+  const int reps = pairsum ? 2 : 1;
+  for (int q = 0; q < reps; ++q) {
+    const long long r = pairsum ? (2 * ro + q) : ro;
+    float a[VEC];
+    *reinterpret_cast<vec*>(a) = reinterpret_cast<const vec*>(dxl)[r * fg + f];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = a[e];
+      if (g_res != nullptr) {
+        const int fe = f * VEC + e;
+        for (int p = t_ptr[fe]; p < t_ptr[fe + 1]; ++p) t = fmaf(t_w[p], g_res[r * res_Fout + t_idx[p]], t);
+      }
+      total[e] += t;
+    }
+  }
+  *reinterpret_cast<vec*>(out + (ro * fg + f) * VEC) = *reinterpret_cast<vec*>(total);
+}
+int launch_dx_finish(const float* dxl, int rows, int F, const float* g_res, int res_Fout, const InterpTable* it,
+                     int out_pairsum, float* out, cudaStream_t s) {
+  const long long rows_out = out_pairsum ? rows / 2 : rows;
+  const bool v4 = (F % 4 == 0) && (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dxl)) & 15) == 0);
+  if (v4)
+    k_dx_finish<4><<<cdiv(rows_out * F / 4, 256), 256, 0, s>>>(dxl, rows_out, F, g_res, res_Fout, it ? it->t_ptr : nullptr,
+                                                              it ? it->t_idx : nullptr, it ? it->t_w : nullptr,
+                                                              out_pairsum, out);
+  else
+    k_dx_finish<1><<<cdiv(rows_out * F, 256), 256, 0, s>>>(dxl, rows_out, F, g_res, res_Fout, it ? it->t_ptr : nullptr,
+                                                          it ? it->t_idx : nullptr, it ? it->t_w : nullptr, out_pairsum,
+                                                          out);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
 // =====================================================================================
 // Generic fp32 GEMM  C = A * op(B)  with the conv epilogue
 // =====================================================================================
@@ -515,6 +564,140 @@ int launch_thin_conv(const DevLevel& g, const float* x, int in_unpool, int rows,
 }
 
 // =====================================================================================
+// Backward of the thin head (Fout <= 4), weights first as well.  With G = [dz | L~ dz | 2 L~ (L~ dz) - dz] (three
+// 4-wide row blocks; L~ is symmetric):
+//     dX[row, f]      = sum_{k,n} G_k[row, n] * W[n, f*3 + k]
+//     dW[n, f*3 + k]  = sum_rows  G_k[row, n] * X[row, f]
+// i.e. the sparse products act on the 3-wide gradient instead of the Fin-wide basis, X is read once, and neither
+// the [rows, 3 Fin] basis nor dT = dz W is ever materialised (the generic path writes and re-reads both).
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_thin_bwd_g1(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                     const float* __restrict__ val, int V, long long rows, int fout,
+                                                     const float* __restrict__ dz, float* __restrict__ G) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int v = (int)(r % V);
+  float g0[4] = {0.f, 0.f, 0.f, 0.f}, g1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = 0; n < fout; ++n) g0[n] = dz[r * fout + n];
+  for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) {
+    const float* d = dz + (r + reloff[p]) * fout;
+    const float w = val[p];
+    for (int n = 0; n < fout; ++n) g1[n] = fmaf(w, d[n], g1[n]);
+  }
+  float4* g = reinterpret_cast<float4*>(G + r * 12);
+  g[0] = make_float4(g0[0], g0[1], g0[2], g0[3]);
+  g[1] = make_float4(g1[0], g1[1], g1[2], g1[3]);
+}
+__global__ void __launch_bounds__(256) k_thin_bwd_g2(const int* __restrict__ rowptr, const int* __restrict__ reloff,
+                                                     const float* __restrict__ val, int V, long long rows,
+                                                     float* __restrict__ G) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int v = (int)(r % V);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = rowptr[v]; p < rowptr[v + 1]; ++p) {
+    const float4 g1 = reinterpret_cast<const float4*>(G + (r + reloff[p]) * 12)[1];
+    const float w = 2.f * val[p];
+    acc.x = fmaf(w, g1.x, acc.x); acc.y = fmaf(w, g1.y, acc.y); acc.z = fmaf(w, g1.z, acc.z); acc.w = fmaf(w, g1.w, acc.w);
+  }
+  float4* g = reinterpret_cast<float4*>(G + r * 12);
+  const float4 g0 = g[0];
+  g[2] = make_float4(acc.x - g0.x, acc.y - g0.y, acc.z - g0.z, acc.w - g0.w);
+}
+// wt[f][4k + n] = W[n][f*3 + k]  (zero for n >= fout)
+__global__ void k_thin_bwd_prep(const float* __restrict__ W, int fin, int fout, float* __restrict__ wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fin * 12) return;
+  const int f = i / 12, j = i % 12, k = j >> 2, n = j & 3;
+  wt[i] = (n < fout) ? W[(size_t)n * fin * 3 + f * 3 + k] : 0.f;
+}
+// Persistent CTAs (256 threads) over 128-row tiles; thread = (row slot 0..15, feature quad 0..FIN/4-1... ) with
+// FIN = 64: 16 quads.  The thread keeps its 4 x 12 weights and its 4 x 12 dW accumulators in registers; G rows
+// come from shared memory (broadcast), X and dX are accessed 256 bytes per row and half-warp (coalesced).
+template <int FIN>
+__global__ void __launch_bounds__(256) k_thin_bwd_main(const float* __restrict__ x, long long rows, int fout,
+                                                       const float* __restrict__ G, const float* __restrict__ wt,
+                                                       float* __restrict__ dx, float* __restrict__ dw) {
+  static_assert(FIN == 64, "one feature quad per lane of a half-warp");
+  __shared__ __align__(16) float gs[128][12];
+  __shared__ float red[12][FIN];
+  const int tid = threadIdx.x;
+  const int q = tid & 15, slot = tid >> 4;
+  float w[4][12], acc[4][12];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      w[e][j] = wt[(4 * q + e) * 12 + j];
+      acc[e][j] = 0.f;
+    }
+  for (int i = tid; i < 12 * FIN; i += 256) (&red[0][0])[i] = 0.f;
+  const long long n_tiles = (rows + 127) / 128;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long r0 = t * 128;
+    __syncthreads();  // the previous tile's readers of gs are done
+    for (int i = tid; i < 128 * 3; i += 256) {
+      const long long r = r0 + i / 3;
+      reinterpret_cast<float4*>(&gs[0][0])[i] =
+          (r < rows) ? reinterpret_cast<const float4*>(G + r * 12)[i % 3] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int rr = slot; rr < 128; rr += 16) {
+      const long long r = r0 + rr;
+      if (r >= rows) break;
+      const float4 g0 = *reinterpret_cast<const float4*>(&gs[rr][0]);
+      const float4 g1 = *reinterpret_cast<const float4*>(&gs[rr][4]);
+      const float4 g2 = *reinterpret_cast<const float4*>(&gs[rr][8]);
+      const float g[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
+      const float4 xv = *reinterpret_cast<const float4*>(x + r * FIN + 4 * q);
+      const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          o[e] = fmaf(g[j], w[e][j], o[e]);
+          acc[e][j] = fmaf(g[j], xe[e], acc[e][j]);
+        }
+      if (dx != nullptr) *reinterpret_cast<float4*>(dx + r * FIN + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int j = 0; j < 12; ++j) atomicAdd(&red[j][4 * q + e], acc[e][j]);
+  __syncthreads();
+  for (int i = tid; i < 12 * FIN; i += 256) {
+    const int j = i / FIN, f = i % FIN, k = j >> 2, n = j & 3;
+    if (n < fout) atomicAdd(dw + (size_t)n * FIN * 3 + f * 3 + k, red[j][f]);
+  }
+}
+bool thin_conv_bwd_supported(int fin, int fout) { return fout <= 4 && fin == 64; }
+size_t thin_conv_bwd_scratch_floats(long long rows, int fin) { return (size_t)rows * 12 + (size_t)fin * 12; }
+int launch_thin_conv_bwd(const DevLevel& g, const float* x, int rows, int fin, int fout, const float* W, const float* dz,
+                         float* scratch, float* dx, float* dw, int sm_count, cudaStream_t s) {
+  if (!thin_conv_bwd_supported(fin, fout)) {
+    set_error("thin_conv_bwd: unsupported shape");
+    return P2M_ERR_INVALID;
+  }
+  float* G = scratch;                       // [rows][12]
+  float* wt = G + (size_t)rows * 12;        // [fin][12]
+  k_thin_bwd_prep<<<cdiv(fin * 12, 128), 128, 0, s>>>(W, fin, fout, wt);
+  P2M_LAUNCH_OK();
+  k_thin_bwd_g1<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, fout, dz, G);
+  P2M_LAUNCH_OK();
+  k_thin_bwd_g2<<<cdiv(rows, 256), 256, 0, s>>>(g.rowptr, g.reloff, g.val, g.V, rows, G);
+  P2M_LAUNCH_OK();
+  P2M_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)fout * 3 * fin, s));
+  const int grid = (int)std::min<long long>(((long long)rows + 127) / 128, (long long)sm_count * 4);
+  k_thin_bwd_main<64><<<grid, 256, 0, s>>>(x, rows, fout, G, wt, dx, dw);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+// =====================================================================================
 // power-of-two scale that brings a tensor into fp16's comfortable range (tensor-core backward GEMMs)
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, long long n, unsigned int* __restrict__ out) {
@@ -568,6 +751,25 @@ int launch_unpermute_w(const float* Wp, float* W, int fout, int fin, cudaStream_
   P2M_LAUNCH_OK();
   return P2M_OK;
 }
+__global__ void __launch_bounds__(256) k_copy_rows(float* __restrict__ y, long long mesh_stride, int F,
+                                                   const int* __restrict__ dst, const int* __restrict__ src, int n,
+                                                   long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, i, f)
+  if (idx >= total) return;
+  const int f = (int)(idx % F);
+  const long long t = idx / F;
+  const int i = (int)(t % n);
+  const long long b = t / n;
+  y[b * mesh_stride + (long long)dst[i] * F + f] = y[b * mesh_stride + (long long)src[i] * F + f];
+}
+int launch_copy_rows(float* y, int batch, int V, int F, const int* dst, const int* src, int n, cudaStream_t s) {
+  if (n <= 0) return P2M_OK;
+  const long long total = (long long)batch * n * F;
+  k_copy_rows<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y, (long long)V * F, F, dst, src, n, total);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t s) {
   P2M_CUDA_OK(cudaMemsetAsync(p, 0, bytes, s));
   return P2M_OK;
@@ -679,8 +881,55 @@ __global__ void __launch_bounds__(256) k_affine_act(const float* __restrict__ z,
   }
   a[idx] = v;
 }
+// four channels per thread (F % 4 == 0, 16-byte aligned tensors); identity residual (res_F == F) as one 16-byte load
+__global__ void __launch_bounds__(256) k_affine_act4(const float4* __restrict__ z, long long n4, int F4,
+                                                     const float4* __restrict__ scale, const float4* __restrict__ shift,
+                                                     int relu, const float* __restrict__ res, int res_F, int res_unpool,
+                                                     const int* __restrict__ i0, const int* __restrict__ i1,
+                                                     const float* __restrict__ lam, float4* __restrict__ a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  const long long r = idx / F4;
+  const int c = (int)(idx - r * F4);
+  float4 v = z[idx];
+  if (scale) {
+    const float4 sc = __ldg(scale + c), sh = __ldg(shift + c);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+  }
+  if (relu) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
+  if (res) {
+    const float* rr = res + (res_unpool ? (r >> 1) : r) * res_F;
+    if (res_F == 4 * F4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(rr) + c);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    } else {
+      float* ve = &v.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = 4 * c + e;
+        const float l = lam[n];
+        ve[e] += (1.f - l) * rr[i0[n]] + l * rr[i1[n]];
+      }
+    }
+  }
+  a[idx] = v;
+}
 int launch_affine_act(const float* z, int rows, int F, const float* scale, const float* shift, int relu,
                       const float* res, int res_F, int res_unpool, const InterpTable* it, float* a, cudaStream_t s) {
+  const bool al = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(scale) |
+                    reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(res)) & 15) == 0;
+  if (F % 4 == 0 && al && (res == nullptr || res_F % 4 == 0)) {
+    const long long n4 = (long long)rows * (F / 4);
+    k_affine_act4<<<cdiv(n4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(z), n4, F / 4,
+                                                reinterpret_cast<const float4*>(scale),
+                                                reinterpret_cast<const float4*>(shift), relu, res, res_F, res_unpool,
+                                                it ? it->i0 : nullptr, it ? it->i1 : nullptr, it ? it->lam : nullptr,
+                                                reinterpret_cast<float4*>(a));
+    P2M_LAUNCH_OK();
+    return P2M_OK;
+  }
   k_affine_act<<<cdiv((long long)rows * F, 256), 256, 0, s>>>(z, rows, F, scale, shift, relu, res, res_F, res_unpool,
                                                              it ? it->i0 : nullptr, it ? it->i1 : nullptr,
                                                              it ? it->lam : nullptr, a);
@@ -749,16 +998,73 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
   float m2 = (float)(sums[F + f] / (double)rows);
   g_z[idx] = gamma[f] * invstd[f] * (g - m1 - zh * m2);
 }
+// four channels per thread; optionally folds max|g_z| into *amax (bits of a non-negative float, atomicMax): the
+// power-of-two scale of the tensor-core backward GEMMs then needs no pass of its own
+__global__ void __launch_bounds__(256) k_bn_bwd_apply4(const float4* __restrict__ z, const float4* __restrict__ g_a,
+                                                       long long n4, int F4, long long rows,
+                                                       const float* __restrict__ gamma, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, int relu,
+                                                       const double* __restrict__ sums, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta, float4* __restrict__ g_z,
+                                                       unsigned int* __restrict__ amax) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int F = 4 * F4;
+  if (idx < F) {
+    dbeta[idx] = (float)sums[idx];
+    dgamma[idx] = (float)sums[F + idx];
+  }
+  float m = 0.f;
+  if (idx < n4) {
+    const int c = (int)(idx % F4);
+    const float4 zv = z[idx];
+    float4 g = g_a[idx];
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+    float gg[4] = {g.x, g.y, g.z, g.w};
+    const double inv_rows = 1.0 / (double)rows;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = 4 * c + e;
+      const float zh = (zz[e] - mean[f]) * invstd[f];
+      if (relu && !(fmaf(zz[e], scale[f], shift[f]) > 0.f)) gg[e] = 0.f;  // exactly the forward's activation test
+      const float m1 = (float)(sums[f] * inv_rows);
+      const float m2 = (float)(sums[F + f] * inv_rows);
+      gg[e] = gamma[f] * invstd[f] * (gg[e] - m1 - zh * m2);
+      m = fmaxf(m, fabsf(gg[e]));
+    }
+    g_z[idx] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+  }
+  if (amax != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+  }
+}
 int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu, double* sums,
-                       float* dgamma, float* dbeta, float* g_z, cudaStream_t s) {
+                       float* dgamma, float* dbeta, float* g_z, cudaStream_t s, float* gz_scale_out) {
   P2M_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s));
   k_bn_bwd_reduce<<<cdiv(rows, STAT_ROWS), 256, 2 * 256 * sizeof(float), s>>>(z, g_a, rows, F, scale, shift, mean,
                                                                                invstd, relu, sums);
   P2M_LAUNCH_OK();
+  const bool al = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(g_a) | reinterpret_cast<uintptr_t>(g_z)) & 15) == 0;
+  if (F % 4 == 0 && al) {
+    if (gz_scale_out) P2M_CUDA_OK(cudaMemsetAsync(gz_scale_out, 0, sizeof(float), s));
+    const long long n4 = (long long)rows * (F / 4);
+    k_bn_bwd_apply4<<<cdiv(std::max<long long>(n4, F), 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(g_a), n4, F / 4, rows, gamma, scale, shift,
+        mean, invstd, relu, sums, dgamma, dbeta, reinterpret_cast<float4*>(g_z),
+        reinterpret_cast<unsigned int*>(gz_scale_out));
+    P2M_LAUNCH_OK();
+    if (gz_scale_out) {
+      k_scale_from_absmax<<<1, 1, 0, s>>>(reinterpret_cast<unsigned int*>(gz_scale_out));
+      P2M_LAUNCH_OK();
+    }
+    return P2M_OK;
+  }
   k_bn_bwd_apply<<<cdiv((long long)rows * F, 256), 256, 0, s>>>(z, g_a, rows, F, gamma, scale, shift, mean, invstd, relu,
                                                                sums, dgamma, dbeta, g_z);
   P2M_LAUNCH_OK();
+  if (gz_scale_out) return launch_absmax_scale(g_z, (long long)rows * F, gz_scale_out, s);
   return P2M_OK;
 }
 

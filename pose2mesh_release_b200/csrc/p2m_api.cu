@@ -56,6 +56,10 @@ struct p2m_model {
   int elide_padding = 1;         // tcgen05 conv: isolated padding vertices through a plain GEMM with combined weights;
                                  // 1 = on levels where they are >= 40 % of the rows (measured break-even), 2 = wherever
                                  // the tile families exist, 0 = off (p2m_debug_set_elide_padding)
+  int dedup_padding = 1;         // eval: among the isolated rows only one representative per class of identical rows is
+                                 // computed (DevLevel::rep_tiles); needs elide_padding == 1 (p2m_debug_set_dedup_padding)
+  int dw_swap = 1;               // backward: dW from the basis of the gradient, re-using the backward-data pass's L~dz
+                                 // (launch_umma_dw_swapped); 0 = rebuild the basis of the layer input (p2m_debug_set_dw_swap)
   int fuse_head = 1;             // eval: the 128 -> 64 conv's epilogue feeds the 64 -> 3 head directly (no 64-wide tensor)
   int split_t1 = 1;              // tcgen05 conv: T1 = L~x in a separate pass (k_cheb_t1) instead of on-chip halo recompute
   int profiling = 0;             // record a CUDA event pair around every conv layer of the eval forward
@@ -169,6 +173,7 @@ struct Sizes {
   size_t max_U = 0;      // floats: max rows*fin
   size_t max_w = 0;      // floats: max fout*3*fin
   size_t max_wpack = 0;  // bytes: packed fp16 hi/lo weight image of the tcgen05 path
+  size_t max_thin = 1;   // floats: scratch of the thin head's backward
   int max_f = 0;
 };
 
@@ -184,6 +189,7 @@ Sizes model_sizes(const p2m_model* m, int B) {
     if (umma_conv_supported(m->levels[L.level], L.fin, L.fout))
       s.max_wpack = std::max(s.max_wpack, umma_wpack_bytes(L.fin, L.fout));
     s.max_f = std::max(s.max_f, std::max(L.fin, L.fout));
+    if (thin_conv_bwd_supported(L.fin, L.fout)) s.max_thin = std::max(s.max_thin, thin_conv_bwd_scratch_floats(rows, L.fin));
   }
   s.max_act = std::max(s.max_act, (size_t)B * m->fc_out);
   s.max_act = std::max(s.max_act, (size_t)B * m->fc_in);
@@ -247,8 +253,10 @@ struct BwdMap {
   float* U;
   float* dwp;
   double* sums;
-  unsigned char* wpack;   // packed fp16 K-blocks of one W_k^T (tcgen05 dT GEMM)
+  unsigned char* wpack;   // packed fp16 K-blocks of the backward-data conv (or of one W_k^T for the dT GEMM fallback)
   size_t wpack_bytes;
+  unsigned char* wpack_iso;  // combined transposed weights of the isolated rows (padding-vertex elision)
+  float* thin;               // scratch of the thin head's backward
   float* a_scale;         // power-of-two gradient scale (device scalar)
   size_t bytes;
 };
@@ -260,8 +268,10 @@ BwdMap map_scratch(const p2m_model* m, int B, void* base) {
   w.U = b.take<float>(s.max_U);
   w.dwp = b.take<float>(std::max(s.max_w, (size_t)1));
   w.sums = b.take<double>(2 * (size_t)s.max_f + 2 * (size_t)m->fc_out);
-  w.wpack_bytes = umma_plain_pack_bytes(256, 256);
+  w.wpack_bytes = umma_wpack_bytes(256, 256);   // backward-data conv image (>= the plain image of one W_k^T)
   w.wpack = b.take<unsigned char>(w.wpack_bytes);
+  w.wpack_iso = b.take<unsigned char>(umma_plain_pack_bytes(256, 256));
+  w.thin = b.take<float>(s.max_thin);
   w.a_scale = b.take<float>(4);
   w.bytes = b.off;
   return w;
@@ -274,7 +284,8 @@ bool conv_on_tensor_cores(const p2m_model* m, const Layer& L, const unsigned cha
 }
 int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpool, const float* w_ref, float* T,
                 float* wp, unsigned char* wpack, const Epilogue& ep, float* y, cudaStream_t s,
-                const float* head_wt = nullptr, float* head_z = nullptr, bool keep_wp = true, bool may_elide = false) {
+                const float* head_wt = nullptr, float* head_z = nullptr, bool keep_wp = true, bool may_elide = false,
+                int iso_mode = 0 /* 0: every isolated row, 1: class representatives only, 2: none */) {
   const int rows = B * L.V;
   const DevLevel& g = m->levels[L.level];
   // k-major copy of the weights: what the SIMT GEMM reads, and (training, keep_wp) what backward's SIMT dT GEMM reads
@@ -306,11 +317,13 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
     if (!elide) return launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s);
     a.tiles = &g.real_tiles;
     P2M_TRY(launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s));
+    if (iso_mode == 2) return P2M_OK;  // nothing the caller reads depends on the isolated rows (gathered eval output)
+    const bool reps_only = (iso_mode == 1 && g.n_rep > 0);
     unsigned char* w_iso = reinterpret_cast<unsigned char*>(T + (size_t)rows * L.fin);
     P2M_TRY(launch_umma_pack_iso(w_ref, g.iso_diag, L.fin, L.fout, w_iso, s));
     a.t1 = nullptr;
     a.plain = 1;
-    a.tiles = &g.iso_tiles;
+    a.tiles = reps_only ? &g.rep_tiles : &g.iso_tiles;
     a.wpack = w_iso;
     return launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s);
   }
@@ -324,6 +337,76 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
   }
   P2M_TRY(launch_cheb_basis(g, x, in_unpool, rows, L.fin, T, s));
   P2M_TRY(launch_gemm(T, 3 * L.fin, wp, 3 * L.fin, 0, y, L.fout, rows, L.fout, 3 * L.fin, ep, s));
+  return P2M_OK;
+}
+
+// The default elision policy (elide_padding == 1): levels that have the tile families and where at least 40 % of
+// the rows are isolated.
+inline bool policy_elided(const DevLevel& g) { return g.n_iso > 0 && 5LL * g.n_iso >= 2LL * g.V; }
+
+// Classes of identical isolated rows (eval mode, DevLevel::rep_tiles).  Levels are ordered fine -> coarse, the joint
+// graph last; the parent of row r of mesh level k is row r >> 1 of level k + 1 (nearest x2 unpool, meshnet.py:71-78).
+// An isolated row is a REPRESENTATIVE if its parent is a connected row (nothing to share), or if it is the left
+// child of a parent whose value is computed (any row of a level that is not elided, a representative otherwise);
+// every other isolated row equals a representative: its left sibling, or the left child of its parent's
+// representative.  Requires what the reference's binary-tree reorder guarantees (lib/coarsening.py:214-258: fake
+// nodes are added bottom-up, so both children of a fake node are fake); if a level violates it the classes are
+// simply not built (n_rep stays 0) and every isolated row is computed.
+int build_padding_classes(p2m_model* m, const p2m_model_desc_t* d) {
+  const int n_mesh = d->n_levels - 1;  // the last level is the joint graph
+  std::vector<std::vector<char>> iso(n_mesh);
+  for (int k = 0; k < n_mesh; ++k) {
+    const int V = d->level_size[k];
+    const int32_t* rp = d->rowptr[k];
+    iso[k].assign(V, 0);
+    for (int v = 0; v < V; ++v) iso[k][v] = (rp[v + 1] - rp[v] == 1 && d->colidx[k][rp[v]] == v) ? 1 : 0;
+  }
+  std::vector<std::vector<int>> rep_of(n_mesh);  // per elided level: representative of each isolated row (itself if rep)
+  for (int k = n_mesh - 1; k >= 0; --k) {
+    DevLevel& g = m->levels[k];
+    if (!policy_elided(g)) continue;
+    const int V = g.V;
+    const bool has_parent = (k + 1 < n_mesh) && (d->level_size[k + 1] * 2 == V);
+    const bool parent_elided = has_parent && policy_elided(m->levels[k + 1]);
+    std::vector<int>& ro = rep_of[k];
+    ro.assign(V, -1);
+    std::vector<int> reps, cdst, csrc;
+    bool ok = true;
+    for (int r = 0; r < V && ok; ++r) {
+      if (!iso[k][r]) continue;
+      const int p = r >> 1;
+      if (!has_parent || !iso[k + 1][p]) {
+        ro[r] = r;
+      } else {
+        if (!iso[k][r ^ 1]) ok = false;  // both children of a fake vertex must be fake
+        const bool parent_computed = !parent_elided || rep_of[k + 1][p] == p;
+        if (parent_computed) ro[r] = r & ~1;
+        else ro[r] = 2 * rep_of[k + 1][p];
+        if (ro[r] < 0 || ro[r] >= V || !iso[k][ro[r]]) ok = false;
+      }
+      if (ro[r] == r) reps.push_back(r);
+      else {
+        cdst.push_back(r);
+        csrc.push_back(ro[r]);
+      }
+    }
+    for (size_t i = 0; i < csrc.size() && ok; ++i)
+      if (ro[csrc[i]] != csrc[i]) ok = false;  // a representative represents itself
+    if (!ok || cdst.empty()) {
+      ro.assign(V, -1);  // treat the level as fully computed
+      for (int r = 0; r < V; ++r)
+        if (iso[k][r]) ro[r] = r;
+      continue;
+    }
+    P2M_TRY(build_index_tiles(reps, d->rowptr[k], d->colidx[k], d->values[k], V, &g.rep_tiles, &m->owned));
+    P2M_TRY(upload(m, cdst, &g.copy_dst));
+    P2M_TRY(upload(m, csrc, &g.copy_src));
+    g.n_rep = (int)reps.size();
+    g.n_copy = (int)cdst.size();
+  }
+  // a level's classes assume that its elided parent level is deduplicated too: keep them only in a chain from the
+  // finest level down (n_rep == 0 on a level switches its children back to "parent fully computed" == still valid,
+  // because a fully computed parent only adds valid rows)
   return P2M_OK;
 }
 
@@ -411,6 +494,13 @@ int p2m_model_create(const p2m_model_desc_t* d, p2m_model_t** out) {
       return st;
     }
     m->levels.push_back(g);
+  }
+  if (d->n_blocks != 0) {
+    int st = build_padding_classes(m, d);
+    if (st) {
+      p2m_model_destroy(m);
+      return st;
+    }
   }
   {
     std::vector<float> zrow(64, 0.f);
@@ -560,6 +650,16 @@ int p2m_debug_set_elide_padding(p2m_model_t* m, int enable) {
   m->elide_padding = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return P2M_OK;
 }
+int p2m_debug_set_dedup_padding(p2m_model_t* m, int enable) {
+  if (!m) return P2M_ERR_INVALID;
+  m->dedup_padding = enable ? 1 : 0;
+  return P2M_OK;
+}
+int p2m_debug_set_dw_swap(p2m_model_t* m, int enable) {
+  if (!m) return P2M_ERR_INVALID;
+  m->dw_swap = enable ? 1 : 0;
+  return P2M_OK;
+}
 int p2m_debug_set_fuse_head(p2m_model_t* m, int enable) {
   if (!m) return P2M_ERR_INVALID;
   m->fuse_head = enable ? 1 : 0;
@@ -638,6 +738,9 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
   }
   const int nb = (int)m->blocks.size();
   const int nl = (int)m->layers.size();
+  // isolated (padding) rows in eval mode: only class representatives (DevLevel::rep_tiles), or — when the caller
+  // takes the gathered real vertices — none at all: no connected row ever reads an isolated one
+  const int iso_mode = (training || !m->dedup_padding || m->elide_padding < 1) ? 0 : (gathered ? 2 : 1);
   const float* cur = x;
   int cur_unpool = 0;
   int cur_buf = -1;  // rotating buffer id holding `cur` (eval)
@@ -713,11 +816,11 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
           float* wt = Z + (size_t)rows * 16;
           P2M_TRY(launch_thin_prep(P->cl_w[li + 1], L.fout, m->layers[li + 1].fout, wt, s));
           P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, wt, Z,
-                              false, true));
+                              false, true, iso_mode));
           head_z = Z;
         } else {
           P2M_TRY(conv_linear(m, L, B, cur, cur_unpool, P->cl_w[li], w.T, w.wp_scratch, w.wpack, ep, out, s, nullptr,
-                              nullptr, false, true));
+                              nullptr, false, true, iso_mode));
         }
         if (m->profiling) P2M_CUDA_OK(cudaEventRecord(m->ev_end[li], s));
         cur = out;
@@ -765,6 +868,11 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
     } else if (blk.out_unpool) {
       cur_unpool = 1;  // nearest x2 unpool is virtual: the next block reads row r>>1
     }
+  }
+  if (iso_mode == 1 && m->levels[0].n_copy > 0) {
+    // fill the output rows of the isolated vertices that were represented by another row of their class
+    const DevLevel& g0 = m->levels[0];
+    P2M_TRY(launch_copy_rows(y, B, g0.V, m->cout, g0.copy_dst, g0.copy_src, g0.n_copy, s));
   }
   return P2M_OK;
 }
@@ -899,38 +1007,120 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params
         keep_buf = g_cur_buf;
         keep_ptr = g_cur;
       }
+      const bool tc = (m->precision == P2M_PREC_FP16X3_TC);
+      const bool need_dx = !(li == 0 && dx == nullptr);
+      const bool res_here = (j == 0) && blk.has_residual;
+      // which path takes this layer's weight / data gradients
+      const bool thin = thin_conv_bwd_supported(L.fin, L.fout) && !in_unpool && !res_here && li > 0;
+      const bool tc_dw = tc && !thin && umma_dw_supported(g, L.fin, L.fout);
+      const bool tc_dx = tc && !thin && need_dx && m->split_t1 && umma_conv_supported(g, L.fout, L.fin) &&
+                         umma_wpack_bytes(L.fout, L.fin) <= sc.wpack_bytes && (size_t)L.fout <= 3 * (size_t)L.fin;
+      const bool tc_dt = tc && !thin && need_dx && !tc_dx && umma_conv_supported(g, L.fout, L.fin) &&
+                         umma_plain_pack_bytes(L.fin, L.fout) <= sc.wpack_bytes;
+      const bool dw_swapped = tc_dx && m->dw_swap && umma_dw_swapped_supported(g, L.fin, L.fout);
+      const bool want_scale = tc_dw || tc_dx || tc_dt;
+      bool have_scale = false;
       if (L.bn) {
         int tgt = (g_cur_buf >= 0 && g_cur_buf != keep_buf) ? g_cur_buf : free_buf(g_cur_buf, keep_buf, -1);
         P2M_TRY(launch_bn_relu_bwd(w.z[li], g_cur, rows, L.fout, P->bn_w[li], w.scale[li], w.shift[li], w.mean[li],
-                                   w.invstd[li], L.relu, sc.sums, G->bn_w[li], G->bn_b[li], sc.G[tgt], s));
+                                   w.invstd[li], L.relu, sc.sums, G->bn_w[li], G->bn_b[li], sc.G[tgt], s,
+                                   want_scale ? sc.a_scale : nullptr));
+        have_scale = want_scale;
         g_z = sc.G[tgt];
         gz_buf = tgt;
-      }
-      P2M_TRY(launch_col_sum(g_z, rows, L.fout, sc.sums, G->cl_b[li], s));
-      // dW.  tcgen05 path: the basis is rebuilt on chip by the forward's producers and contracted with the
-      // (power-of-two scaled) dz tile by MN-major UMMAs; otherwise SIMT: materialise T, dWp = g_z^T T.
-      const bool tc = (m->precision == P2M_PREC_FP16X3_TC);
-      bool have_scale = false;
-      if (tc && umma_dw_supported(g, L.fin, L.fout)) {
-        P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
-        have_scale = true;
-        P2M_TRY(launch_fill_zero(G->cl_w[li], sizeof(float) * L.fout * 3 * L.fin, s));
-        P2M_TRY(launch_umma_dw(g, inp, in_unpool, B, L.fin, L.fout, g_z, sc.a_scale, G->cl_w[li], m->kernel_status,
-                               m->sm_count, s));
+        // the bias of a conv in front of a BatchNorm has a mathematically zero gradient (the batch mean removes
+        // it): db = sum_rows dz = 0 exactly, where the reference accumulates fp32 rounding noise
+        P2M_TRY(launch_fill_zero(G->cl_b[li], sizeof(float) * L.fout, s));
       } else {
-        P2M_TRY(launch_cheb_basis(g, inp, in_unpool, rows, L.fin, w.T, s));
-        P2M_TRY(launch_fill_zero(sc.dwp, sizeof(float) * L.fout * 3 * L.fin, s));
-        P2M_TRY(launch_gemm_tn_atomic(g_z, L.fout, w.T, 3 * L.fin, sc.dwp, 3 * L.fin, rows, L.fout, 3 * L.fin, s));
-        P2M_TRY(launch_unpermute_w(sc.dwp, G->cl_w[li], L.fout, L.fin, s));
+        P2M_TRY(launch_col_sum(g_z, rows, L.fout, sc.sums, G->cl_b[li], s));
+      }
+      if (want_scale && !have_scale) P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
+      float* out = nullptr;
+      int out_buf = -1;
+      if (need_dx) {
+        if (li == 0) {
+          out = dx;
+        } else {
+          out_buf = free_buf(gz_buf, keep_buf, -1);
+          out = sc.G[out_buf];
+        }
+      }
+      if (thin) {
+        // weights-first backward of the thin head: dW and dX from the 3-wide basis of dz, X read once
+        P2M_TRY(launch_thin_conv_bwd(g, inp, rows, L.fin, L.fout, P->cl_w[li], g_z, sc.thin, out, G->cl_w[li],
+                                     m->sm_count, s));
+      } else {
+        // dW.  tcgen05 path: the basis is rebuilt on chip by the forward's producers and contracted with the
+        // (power-of-two scaled) dz tile by MN-major UMMAs; otherwise SIMT: materialise T, dWp = g_z^T T.
+        if (dw_swapped) {
+          // sum_rows dz (x) T_k(X) = sum_rows T_k(dz) (x) X  (L~ symmetric): the basis of the GRADIENT, whose first
+          // sparse product the backward-data pass below needs anyway, contracted with plain tiles of the layer input
+          P2M_TRY(launch_cheb_t1(g, g_z, 0, B, L.fout, w.T, s, nullptr));
+          P2M_TRY(launch_fill_zero(G->cl_w[li], sizeof(float) * L.fout * 3 * L.fin, s));
+          P2M_TRY(launch_umma_dw_swapped(g, inp, in_unpool, B, L.fin, L.fout, g_z, w.T, sc.a_scale, G->cl_w[li],
+                                         m->kernel_status, m->sm_count, s));
+        } else if (tc_dw) {
+          P2M_TRY(launch_fill_zero(G->cl_w[li], sizeof(float) * L.fout * 3 * L.fin, s));
+          P2M_TRY(launch_umma_dw(g, inp, in_unpool, B, L.fin, L.fout, g_z, sc.a_scale, G->cl_w[li], m->kernel_status,
+                                 m->sm_count, s));
+        } else {
+          P2M_TRY(launch_cheb_basis(g, inp, in_unpool, rows, L.fin, w.T, s));
+          P2M_TRY(launch_fill_zero(sc.dwp, sizeof(float) * L.fout * 3 * L.fin, s));
+          P2M_TRY(launch_gemm_tn_atomic(g_z, L.fout, w.T, 3 * L.fin, sc.dwp, 3 * L.fin, rows, L.fout, 3 * L.fin, s));
+          P2M_TRY(launch_unpermute_w(sc.dwp, G->cl_w[li], L.fout, L.fin, s));
+        }
       }
       // dX
-      const bool need_dx = !(li == 0 && dx == nullptr);
-      if (need_dx) {
+      if (need_dx && tc_dx) {
+        // Backward-data IS a forward conv: dXl = [dz | L~dz | (2L~^2 - I)dz] W'^T with W'[f][o*3+k] = W[o][f*3+k]
+        // (L~ symmetric) — the T1 pass and the tcgen05 conv kernel of the forward, run on dz (scaled into fp16's
+        // range by a power of two), with the padding-vertex elision of the forward.  An identity residual gradient
+        // is added in the epilogue; the pair-sum of the virtual unpool and a resampled residual need a finishing pass.
+        const bool identity_res = res_here && blk.cin == blk.cout;
+        const bool finish = in_unpool || (res_here && !identity_res);
+        float* dst = finish ? sc.U : out;
+        const bool elide = m->elide_padding && g.n_iso > 0 && rows >= 2 * L.fin &&
+                           (m->elide_padding >= 2 || 5LL * g.n_iso >= 2LL * g.V);
+        if (!dw_swapped)  // (the swapped dW above already left L~dz of every row in w.T)
+          P2M_TRY(launch_cheb_t1(g, g_z, 0, B, L.fout, w.T, s, elide ? &g.real_tiles : nullptr));
+        P2M_TRY(launch_umma_pack_weights_t(P->cl_w[li], L.fin, L.fout, sc.wpack, s));
+        UmmaConvArgs a;
+        a.g = &g;
+        a.x = g_z;
+        a.in_unpool = 0;
+        a.batch = B;
+        a.fin = L.fout;
+        a.fout = L.fin;
+        a.wpack = sc.wpack;
+        a.t1 = w.T;
+        a.a_scale = sc.a_scale;
+        a.y = dst;
+        if (identity_res) {
+          a.ep.res = keep_ptr;
+          a.ep.res_F = blk.cout;
+          a.ep.res_unpool = 0;
+          a.ep.res_i0 = blk.interp.i0;
+          a.ep.res_i1 = blk.interp.i1;
+          a.ep.res_lam = blk.interp.lam;
+        }
+        if (elide) a.tiles = &g.real_tiles;
+        P2M_TRY(launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s));
+        if (elide) {
+          P2M_TRY(launch_umma_pack_iso_t(P->cl_w[li], g.iso_diag, L.fin, L.fout, sc.wpack_iso, s));
+          a.t1 = nullptr;
+          a.plain = 1;
+          a.tiles = &g.iso_tiles;
+          a.wpack = sc.wpack_iso;
+          P2M_TRY(launch_umma_conv(a, m->kernel_status, m->zero_row, m->sm_count, s));
+        }
+        if (finish)
+          P2M_TRY(launch_dx_finish(dst, rows, L.fin, (res_here && !identity_res) ? keep_ptr : nullptr, blk.cout,
+                                   (res_here && !identity_res) ? &blk.interp : nullptr, in_unpool, out, s));
+      } else if (need_dx && !thin) {
         Epilogue none;
-        // dT = g_z * Wp  ([rows, Fout] x [Fout, 3 Fin]).  tcgen05 path: three plain GEMMs (one per Chebyshev
+        // dT = g_z * Wp  ([rows, Fout] x [Fout, 3 Fin]).  tcgen05 fallback: three plain GEMMs (one per Chebyshev
         // order, N = Fin, K = Fout) with the gradient scaled into fp16 range by a power of two.
-        if (tc && umma_conv_supported(g, L.fout, L.fin) && umma_plain_pack_bytes(L.fin, L.fout) <= sc.wpack_bytes) {
-          if (!have_scale) P2M_TRY(launch_absmax_scale(g_z, (long long)rows * L.fout, sc.a_scale, s));
+        if (tc_dt) {
           for (int k = 0; k < 3; ++k) {
             // B_k[n = f][kk = o] = W[o, f*3 + k]   (reference layout, lib/models/backbones/cheby_graph_conv.py:32-37)
             P2M_TRY(launch_umma_pack_plain(P->cl_w[li] + k, 3, 3LL * L.fin, L.fin, L.fout, sc.wpack, s));
@@ -952,17 +1142,10 @@ int p2m_meshnet_backward(p2m_model_t* m, const p2m_params_t* P, const p2m_params
         } else {
           P2M_TRY(launch_gemm(g_z, L.fout, w.wp[li], 3 * L.fin, 1, w.T, 3 * L.fin, rows, 3 * L.fin, L.fout, none, s));
         }
-        const bool res_here = (j == 0) && blk.has_residual;
-        float* out;
-        int out_buf = -1;
-        if (li == 0) {
-          out = dx;
-        } else {
-          out_buf = free_buf(gz_buf, keep_buf, -1);
-          out = sc.G[out_buf];
-        }
         P2M_TRY(launch_cheb_basis_bwd(g, w.T, rows, L.fin, sc.U, res_here ? keep_ptr : nullptr, blk.cout,
                                       res_here ? &blk.interp : nullptr, in_unpool, out, s));
+      }
+      if (need_dx) {
         g_cur = out;
         g_cur_buf = out_buf;
       }
@@ -1122,6 +1305,392 @@ int p2m_cheb_conv_bwd(p2m_model_t* m, const p2m_conv_bwd_args_t* a, void* worksp
     }
     P2M_TRY(launch_cheb_basis_bwd(g, T, (int)rows, fin, U, nullptr, 0, nullptr, 0, a->dx, s));
   }
+  return P2M_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// Row f1 of SURVEY.md §8: what FlatPose2Mesh runs in front of MeshNet (lib/models/pose2mesh_net.py:16-22) —
+// the PoseNet 2-D -> 3-D lifter (lib/models/posenet.py:41-87, eval mode: running-stat BatchNorm, dropout off) and
+// the concat  pose_combine = cat(pose2d, pose3d / 1000)  that becomes MeshNet's input.
+//   y  = x W1^T + b1                                                  [B, H]
+//   per stage:  y += relu(bn2(relu(bn1(y)) Wa^T + ba)) Wb^T + bb
+//   pose3d = y W2^T + b2                                              [B, 3J]
+// fp32 FFMA GEMMs (k_gemm) with the BatchNorm / ReLU / residual fused into the epilogues; B rows only, so the
+// 4 H x H weight matrices (64 MB each at H = 4096) dominate the traffic and are read once per call.
+// =====================================================================================
+namespace {
+__global__ void __launch_bounds__(256) k_bn_relu_rows(const float* __restrict__ x, long long n, int F,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ rm, const float* __restrict__ rv,
+                                                      float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = (int)(i % F);
+  const float sc = gamma[f] / sqrtf(rv[f] + 1e-5f);
+  y[i] = fmaxf(fmaf(x[i] - rm[f], sc, beta[f]), 0.f);
+}
+__global__ void __launch_bounds__(256) k_pose_combine(const float* __restrict__ pose2d, const float* __restrict__ pose3d,
+                                                      long long n_joint_rows, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
+  if (i >= n_joint_rows) return;
+  out[i * 5 + 0] = pose2d[i * 2 + 0];
+  out[i * 5 + 1] = pose2d[i * 2 + 1];
+  out[i * 5 + 2] = pose3d[i * 3 + 0] / 1000.f;
+  out[i * 5 + 3] = pose3d[i * 3 + 1] / 1000.f;
+  out[i * 5 + 4] = pose3d[i * 3 + 2] / 1000.f;
+}
+}  // namespace
+
+extern "C" {
+
+size_t p2m_posenet_workspace_bytes(int batch, int hidden) {
+  if (batch <= 0 || hidden <= 0) return 0;
+  return 3 * align_up((size_t)batch * hidden * 4) + align_up(2 * (size_t)hidden * 4);
+}
+
+int p2m_posenet_forward(const p2m_posenet_params_t* P, const float* pose2d, float* pose3d, float* pose_combine, int B,
+                        void* workspace, size_t workspace_bytes, p2m_stream_t stream) {
+  if (!P || !pose2d || !pose3d || B <= 0 || !workspace || P->num_joint <= 0 || P->hidden <= 0 || P->num_stage < 0 ||
+      !P->w1_w || !P->w1_b || !P->w2_w || !P->w2_b) {
+    set_error("posenet_forward: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  if (workspace_bytes < p2m_posenet_workspace_bytes(B, P->hidden)) {
+    set_error("posenet_forward: workspace too small");
+    return P2M_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int H = P->hidden, J = P->num_joint;
+  Bump b(workspace);
+  float* y = b.take<float>((size_t)B * H);
+  float* a = b.take<float>((size_t)B * H);
+  float* h = b.take<float>((size_t)B * H);
+  float* sc = b.take<float>(2 * (size_t)H);
+  Epilogue e1;
+  e1.bias = P->w1_b;
+  P2M_TRY(launch_gemm(pose2d, 2 * J, P->w1_w, 2 * J, 0, y, H, B, H, 2 * J, e1, s));
+  for (int st = 0; st < P->num_stage; ++st) {
+    const p2m_posenet_stage_t& S = P->stages[st];
+    if (!S.w1_w || !S.w1_b || !S.w2_w || !S.w2_b || !S.bn1_w || !S.bn1_b || !S.bn1_rm || !S.bn1_rv || !S.bn2_w ||
+        !S.bn2_b || !S.bn2_rm || !S.bn2_rv) {
+      set_error("posenet_forward: null stage tensor");
+      return P2M_ERR_INVALID;
+    }
+    // a = relu(bn1(y))
+    const long long n = (long long)B * H;
+    k_bn_relu_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, n, H, S.bn1_w, S.bn1_b, S.bn1_rm, S.bn1_rv, a);
+    P2M_LAUNCH_OK();
+    // h = relu(bn2(a Wa^T + ba)): BatchNorm folded into the GEMM epilogue
+    P2M_TRY(launch_bn_fold_eval(S.bn2_w, S.bn2_b, S.bn2_rm, S.bn2_rv, S.w1_b, sc, sc + H, H, s));
+    Epilogue ea;
+    ea.scale = sc;
+    ea.shift = sc + H;
+    ea.relu = 1;
+    P2M_TRY(launch_gemm(a, H, S.w1_w, H, 0, h, H, B, H, H, ea, s));
+    // y' = y + h Wb^T + bb  (written to `a`, then the buffers swap roles)
+    Epilogue eb;
+    eb.bias = S.w2_b;
+    eb.res = y;
+    eb.res_F = H;
+    P2M_TRY(launch_gemm(h, H, S.w2_w, H, 0, a, H, B, H, H, eb, s));
+    std::swap(y, a);
+  }
+  Epilogue e2;
+  e2.bias = P->w2_b;
+  P2M_TRY(launch_gemm(y, H, P->w2_w, H, 0, pose3d, 3 * J, B, 3 * J, H, e2, s));
+  if (pose_combine != nullptr) {
+    const long long n = (long long)B * J;
+    k_pose_combine<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pose2d, pose3d, n, pose_combine);
+    P2M_LAUNCH_OK();
+  }
+  return P2M_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// Row f2 of SURVEY.md §8: the steps either side of the model in the reference's callers.
+//  * joint regression  joints = J_regressor @ vertices   (lib/core/base.py:131,204; demo/run.py:171)
+//  * the demo's input normalisation, demo/run.py:150-158: tight box of the 2-D joints (coord_utils.py:21-39) ->
+//    aspect-preserving box of the network input (process_bbox, :42-66) -> affine map into the input_w x input_h
+//    patch (aug_utils.py:51-64,140-179 with rot = 0: a uniform scaling that maps the box centre to the patch
+//    centre) -> divide by the patch size -> per-pose zero mean / unit std per coordinate.
+// =====================================================================================
+namespace {
+__global__ void __launch_bounds__(256) k_regress_joints(const float* __restrict__ Jr, const float* __restrict__ verts,
+                                                        int n_vertex, int chans, float* __restrict__ joints) {
+  // one CTA per (joint, mesh); chans <= 4
+  const int j = blockIdx.x, n_joint = gridDim.x;
+  const long long b = blockIdx.y;
+  const float* jr = Jr + (size_t)j * n_vertex;
+  const float* vb = verts + b * (long long)n_vertex * chans;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int v = threadIdx.x; v < n_vertex; v += 256) {
+    const float w = __ldg(jr + v);
+    for (int c = 0; c < chans; ++c) acc[c] = fmaf(w, vb[(long long)v * chans + c], acc[c]);
+  }
+  __shared__ float red[4][8];
+  for (int c = 0; c < 4; ++c) {
+    float a = acc[c];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[c][threadIdx.x >> 5] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < chans) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
+    joints[(b * n_joint + j) * chans + threadIdx.x] = a;
+  }
+}
+
+// one warp per pose, lane = joint (n_joint <= 32)
+__global__ void __launch_bounds__(128) k_normalize_pose2d(const float* __restrict__ px, int batch, int n_joint, int in_h,
+                                                          int in_w, int truncate, float* __restrict__ out) {
+  const int pose = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pose >= batch) return;
+  const bool on = lane < n_joint;
+  const float x = on ? px[((long long)pose * n_joint + lane) * 2 + 0] : 0.f;
+  const float y = on ? px[((long long)pose * n_joint + lane) * 2 + 1] : 0.f;
+  float xmin = on ? x : INFINITY, xmax = on ? x : -INFINITY, ymin = on ? y : INFINITY, ymax = on ? y : -INFINITY;
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  // get_bbox (float32 arithmetic like numpy on the float32 box)
+  float bx, by, bw, bh;
+  {
+    const double xc = ((double)xmin + (double)xmax) / 2.0, w = (double)xmax - (double)xmin;
+    const double yc = ((double)ymin + (double)ymax) / 2.0, h = (double)ymax - (double)ymin;
+    bx = (float)(xc - 0.5 * w); by = (float)(yc - 0.5 * h); bw = (float)w; bh = (float)h;
+  }
+  // process_bbox: sanitise (x2 = x + (w - 1)), grow to the aspect ratio width / height, scale 1.0
+  float w = (bx + (bw - 1.f)) - bx, h = (by + (bh - 1.f)) - by;
+  const float cx = bx + w / 2.f, cy = by + h / 2.f;
+  const float aspect = (float)in_w / (float)in_h;
+  if (w > aspect * h) h = w / aspect;
+  else if (w < aspect * h) w = h * aspect;
+  const float x0 = cx - w / 2.f, y0 = cy - h / 2.f;
+  // get_center_scale + get_affine_transform(rot = 0): three float32 point pairs, solved in double
+  const float ccx = x0 + w * 0.5f, ccy = y0 + h * 0.5f;
+  const float s1y = ccy + w * -0.5f;                                     // src[1] = centre + (0, -src_w / 2)
+  const double dst_w = (double)in_w, dst_h = (double)in_h;
+  const float d1y = (float)(dst_h * 0.5) + (float)(dst_w * -0.5);        // dst[1] = (dst_w / 2, dst_h / 2 - dst_w / 2)
+  const double sc = ((double)d1y - dst_h * 0.5) / ((double)s1y - (double)ccy);
+  double tx = ((double)x - (double)ccx) * sc + dst_w * 0.5;
+  double ty = ((double)y - (double)ccy) * sc + dst_h * 0.5;
+  if (truncate) {  // the reference writes the transformed point back into an INTEGER array (demo/h36m_joint_input.npy
+    tx = trunc(tx);  // is int64): truncation towards zero before astype('float32')
+    ty = trunc(ty);
+  }
+  float u = (float)tx / (float)in_w, v = (float)ty / (float)in_h;
+  // per-pose mean / std (population) per coordinate
+  float su = on ? u : 0.f, sv = on ? v : 0.f;
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+  }
+  const float mu = su / n_joint, mv = sv / n_joint;
+  float qu = on ? (u - mu) * (u - mu) : 0.f, qv = on ? (v - mv) * (v - mv) : 0.f;
+  for (int o = 16; o > 0; o >>= 1) {
+    qu += __shfl_xor_sync(0xffffffffu, qu, o);
+    qv += __shfl_xor_sync(0xffffffffu, qv, o);
+  }
+  if (on) {
+    out[((long long)pose * n_joint + lane) * 2 + 0] = (u - mu) / sqrtf(qu / n_joint);
+    out[((long long)pose * n_joint + lane) * 2 + 1] = (v - mv) / sqrtf(qv / n_joint);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int p2m_regress_joints(const float* joint_regressor, const float* vertices, float* joints, int batch, int n_joint,
+                       int n_vertex, int chans, p2m_stream_t stream) {
+  if (!joint_regressor || !vertices || !joints || batch <= 0 || n_joint <= 0 || n_vertex <= 0 || chans <= 0 || chans > 4 ||
+      batch > 65535) {
+    set_error("regress_joints: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  k_regress_joints<<<dim3(n_joint, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(joint_regressor, vertices,
+                                                                                       n_vertex, chans, joints);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+int p2m_normalize_pose2d(const float* joints_px, float* pose2d, int batch, int n_joint, int input_h, int input_w,
+                         int truncate_like_int_input, p2m_stream_t stream) {
+  if (!joints_px || !pose2d || batch <= 0 || n_joint <= 0 || n_joint > 32 || input_h <= 0 || input_w <= 0) {
+    set_error("normalize_pose2d: bad argument (at most 32 joints)");
+    return P2M_ERR_INVALID;
+  }
+  k_normalize_pose2d<<<(batch + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(joints_px, batch, n_joint, input_h,
+                                                                                   input_w, truncate_like_int_input, pose2d);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================
+// Row f3 of SURVEY.md §8: the mesh losses of lib/core/loss.py on the GPU, forward and backward in one pass.
+//   NormalVectorLoss (:62-87)  mean over (B, 3 Nf) of |<normalize(edge_i(out)), normal(gt)>|
+//   EdgeLengthLoss   (:90-114) mean over (B, 3 Nf) of | |edge_i(out)| - |edge_i(gt)| |
+//   CoordLoss        (:10-23)  mean |pred * valid - target * valid|
+// The reference rebuilds a LongTensor of the faces on the device in EVERY call (:68, :97) and materialises ~20
+// [B, Nf, 3] temporaries; here one thread handles one (mesh, face): 18 loads, the two loss terms, and — when
+// gradients are wanted — 9 atomic adds into d(coord_out).  F.normalize semantics: v / max(|v|, 1e-12).
+// =====================================================================================
+namespace {
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 scale3(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 normalize3(V3 a, float* len) {
+  const float n = sqrtf(dot3(a, a));
+  *len = n;
+  return scale3(a, 1.f / fmaxf(n, 1e-12f));
+}
+__device__ __forceinline__ V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ void atomic_add3(float* p, V3 g) {
+  atomicAdd(p + 0, g.x);
+  atomicAdd(p + 1, g.y);
+  atomicAdd(p + 2, g.z);
+}
+
+// sums[0] += sum of the 3 normal terms, sums[1] += sum of the 3 edge terms (fp64); grad (optional, zeroed by the
+// caller) += g_normal * d(normal sum)/d(out) + g_edge * d(edge sum)/d(out) with g_* already divided by 3 B Nf.
+__global__ void __launch_bounds__(256) k_mesh_losses(const float* __restrict__ out, const float* __restrict__ gt,
+                                                     const int* __restrict__ faces, int n_face, int n_vertex, int batch,
+                                                     const float* __restrict__ g_scale, double* __restrict__ sums,
+                                                     float* __restrict__ grad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float ln = 0.f, le = 0.f;
+  if (idx < (long long)batch * n_face) {
+    const int f = (int)(idx % n_face);
+    const long long b = idx / n_face;
+    const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    const float* ob = out + b * (long long)n_vertex * 3;
+    const float* gb = gt + b * (long long)n_vertex * 3;
+    const V3 o0 = ld3(ob + 3 * i0), o1 = ld3(ob + 3 * i1), o2 = ld3(ob + 3 * i2);
+    const V3 t0 = ld3(gb + 3 * i0), t1 = ld3(gb + 3 * i1), t2 = ld3(gb + 3 * i2);
+    // ---- normal-vector term
+    float l1, l2, l3, lg;
+    const V3 e1 = sub3(o1, o0), e2 = sub3(o2, o0), e3 = sub3(o2, o1);
+    const V3 u1 = normalize3(e1, &l1), u2 = normalize3(e2, &l2), u3 = normalize3(e3, &l3);
+    const V3 a = normalize3(sub3(t1, t0), &lg), c = normalize3(sub3(t2, t0), &lg);
+    const V3 n = normalize3(V3{a.y * c.z - a.z * c.y, a.z * c.x - a.x * c.z, a.x * c.y - a.y * c.x}, &lg);
+    const float c1 = dot3(u1, n), c2 = dot3(u2, n), c3 = dot3(u3, n);
+    ln = fabsf(c1) + fabsf(c2) + fabsf(c3);
+    // ---- edge-length term (reference edge order: (0,1), (0,2), (1,2))
+    const float d1 = l1, d2 = l2, d3 = l3;  // |o0-o1|, |o0-o2|, |o1-o2|
+    float q1, q2, q3;
+    normalize3(sub3(t0, t1), &q1);
+    normalize3(sub3(t0, t2), &q2);
+    normalize3(sub3(t1, t2), &q3);
+    const float r1 = d1 - q1, r2 = d2 - q2, r3 = d3 - q3;
+    le = fabsf(r1) + fabsf(r2) + fabsf(r3);
+    if (grad != nullptr) {
+      const float gn = g_scale[0], ge = g_scale[1];
+      float* gr = grad + b * (long long)n_vertex * 3;
+      // d|<u, n>| / de = sign(<u,n>) (n - u <u,n>) / |e|   (|e| > eps); sign(0) = 0 like torch.abs
+      auto dcos = [&](V3 u, float cs, float len) {
+        const float sg = (cs > 0.f) - (cs < 0.f);
+        const float inv = (len > 1e-12f) ? sg / len : 0.f;
+        return scale3(sub3(n, scale3(u, cs)), inv * gn);
+      };
+      // d| |e| - q | / de = sign(|e| - q) e / |e|
+      auto dlen = [&](V3 u, float r, float len) {
+        const float sg = (r > 0.f) - (r < 0.f);
+        return scale3(u, (len > 0.f) ? sg * ge : 0.f);
+      };
+      V3 g1 = dcos(u1, c1, l1), g2 = dcos(u2, c2, l2), g3 = dcos(u3, c3, l3);       // w.r.t. e1, e2, e3
+      const V3 h1 = dlen(u1, r1, l1), h2 = dlen(u2, r2, l2), h3 = dlen(u3, r3, l3);  // same edges (sign-symmetric)
+      g1 = V3{g1.x + h1.x, g1.y + h1.y, g1.z + h1.z};
+      g2 = V3{g2.x + h2.x, g2.y + h2.y, g2.z + h2.z};
+      g3 = V3{g3.x + h3.x, g3.y + h3.y, g3.z + h3.z};
+      // e1 = o1 - o0, e2 = o2 - o0, e3 = o2 - o1
+      atomic_add3(gr + 3 * i0, V3{-g1.x - g2.x, -g1.y - g2.y, -g1.z - g2.z});
+      atomic_add3(gr + 3 * i1, V3{g1.x - g3.x, g1.y - g3.y, g1.z - g3.z});
+      atomic_add3(gr + 3 * i2, V3{g2.x + g3.x, g2.y + g3.y, g2.z + g3.z});
+    }
+  }
+  __shared__ float red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    ln += __shfl_xor_sync(0xffffffffu, ln, o);
+    le += __shfl_xor_sync(0xffffffffu, le, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = ln;
+    red[1][threadIdx.x >> 5] = le;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+// CoordLoss: sums[0] += sum |p v - t v|; grad (optional) = g * sign(p v - t v) * v
+__global__ void __launch_bounds__(256) k_coord_loss(const float* __restrict__ pred, const float* __restrict__ target,
+                                                    const float* __restrict__ valid, long long n,
+                                                    const float* __restrict__ g_scale, double* __restrict__ sums,
+                                                    float* __restrict__ grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (i < n) {
+    const float v = valid ? valid[i] : 1.f;
+    const float d = pred[i] * v - target[i] * v;
+    l = fabsf(d);
+    if (grad != nullptr) grad[i] = g_scale[0] * (float)((d > 0.f) - (d < 0.f)) * v;
+  }
+  __shared__ float red[8];
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(sums, s);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int p2m_mesh_losses(const float* coord_out, const float* coord_gt, const int32_t* faces, int batch, int n_vertex,
+                    int n_face, const float* grad_scale, double* sums, float* grad_out, p2m_stream_t stream) {
+  if (!coord_out || !coord_gt || !faces || !sums || batch <= 0 || n_vertex <= 0 || n_face <= 0 ||
+      (grad_out != nullptr && grad_scale == nullptr)) {
+    set_error("mesh_losses: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  P2M_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
+  if (grad_out) P2M_CUDA_OK(cudaMemsetAsync(grad_out, 0, sizeof(float) * 3 * (size_t)batch * n_vertex, s));
+  const long long n = (long long)batch * n_face;
+  k_mesh_losses<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(coord_out, coord_gt, faces, n_face, n_vertex, batch, grad_scale,
+                                                            sums, grad_out);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+
+int p2m_coord_loss(const float* pred, const float* target, const float* valid, int64_t n, const float* grad_scale,
+                   double* sum, float* grad_out, p2m_stream_t stream) {
+  if (!pred || !target || !sum || n <= 0 || (grad_out != nullptr && grad_scale == nullptr)) {
+    set_error("coord_loss: bad argument");
+    return P2M_ERR_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  P2M_CUDA_OK(cudaMemsetAsync(sum, 0, sizeof(double), s));
+  k_coord_loss<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pred, target, valid, n, grad_scale, sum, grad_out);
+  P2M_LAUNCH_OK();
   return P2M_OK;
 }
 

@@ -79,6 +79,16 @@ struct DevLevel {
   int n_iso = 0;
   float iso_diag = 0.f;
   TileSet real_tiles, iso_tiles;
+  // Eval-mode duplicate elimination among the isolated rows (p2m_api.cu: build_padding_classes).  The two children
+  // of a fake vertex are fake too and, with BatchNorm folded, carry identical values in every layer of their level
+  // (same parent row through the unpool, same dense map): only one REPRESENTATIVE per class is computed
+  // (rep_tiles, plain GEMM like iso_tiles) and the network's output rows of the others are filled from it at the
+  // end (copy_dst[i] <- copy_src[i], finest level only).  n_rep == 0: not applicable on this level.
+  TileSet rep_tiles;
+  int n_rep = 0;
+  int n_copy = 0;
+  int* copy_dst = nullptr;
+  int* copy_src = nullptr;
 };
 
 // 2-tap channel resampling table (F.interpolate(mode='linear', align_corners=False) along channels,
@@ -143,8 +153,12 @@ __device__ __forceinline__ float apply_epilogue(float v, long long r, int n, con
   if (ep.res) {
     long long pr = ep.res_unpool ? (r >> 1) : r;
     const float* rr = ep.res + pr * ep.res_F;
-    float l = ep.lam[n];
-    v += (1.f - l) * rr[ep.i0[n]] + l * rr[ep.i1[n]];
+    if (ep.lam == nullptr) {  // no resampling table: plain residual (res_F == N)
+      v += rr[n];
+    } else {
+      float l = ep.lam[n];
+      v += (1.f - l) * rr[ep.i0[n]] + l * rr[ep.i1[n]];
+    }
   }
   return v;
 }
@@ -162,6 +176,12 @@ bool thin_conv_supported(int fin, int fout);
 size_t thin_conv_scratch_floats(long long rows, int fin);
 int launch_thin_conv(const DevLevel& g, const float* x, int in_unpool, int rows, int fin, int fout, const float* W,
                      const Epilogue& e, float* scratch, float* y, cudaStream_t s);
+// Backward of the thin conv (fin == 64, fout <= 4, no unpool): dx [rows, fin] (may be null), dw [fout, 3 fin] in the
+// reference layout (zeroed here); scratch >= thin_conv_bwd_scratch_floats(rows, fin) floats.
+bool thin_conv_bwd_supported(int fin, int fout);
+size_t thin_conv_bwd_scratch_floats(long long rows, int fin);
+int launch_thin_conv_bwd(const DevLevel& g, const float* x, int rows, int fin, int fout, const float* W, const float* dz,
+                         float* scratch, float* dx, float* dw, int sm_count, cudaStream_t s);
 // The same head in two pieces, for the fused eval path: the 128 -> 64 conv's epilogue produces Z = Y W' itself
 // (head_wt / head_z of UmmaConvArgs), the tail applies the two sparse products on the 4-wide rows.
 int launch_thin_prep(const float* W, int fin, int fout, float* wt, cudaStream_t s);
@@ -171,6 +191,8 @@ int launch_thin_tail(const DevLevel& g, int rows, int fout, const float* Z, floa
 int launch_permute_w(const float* W, float* Wp, int fout, int fin, cudaStream_t s);      // [n,f*3+k] -> [n,k*fin+f]
 int launch_unpermute_w(const float* Wp, float* W, int fout, int fin, cudaStream_t s);    // inverse
 int launch_fill_zero(void* p, size_t bytes, cudaStream_t s);
+// y[b, dst[i], :] = y[b, src[i], :]  for i < n, b < batch  (y [batch, V, F])
+int launch_copy_rows(float* y, int batch, int V, int F, const int* dst, const int* src, int n, cudaStream_t s);
 
 // BatchNorm1d over rows (cheby_graph_conv.py:38-39; meshnet.py:55): eps 1e-5, momentum 0.1
 int launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv, const float* bias,
@@ -185,7 +207,8 @@ int launch_affine_act(const float* z, int rows, int F, const float* scale, const
 // written.  The ReLU mask is recomputed from z (block-end activations already include the residual).
 int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu,
-                       double* sums /*[2F] scratch*/, float* dgamma, float* dbeta, float* g_z, cudaStream_t s);
+                       double* sums /*[2F] scratch*/, float* dgamma, float* dbeta, float* g_z, cudaStream_t s,
+                       float* gz_scale_out = nullptr /* optional device scalar: launch_absmax_scale(g_z) fused in */);
 int launch_col_sum(const float* g, int rows, int F, double* scratch /*[F]*/, float* out, cudaStream_t s);
 
 // dX of the Chebyshev basis: given dT [rows,3F] (blocks dT0|dT1|dT2):
@@ -223,6 +246,9 @@ struct UmmaConvArgs {
 // Host: build the per-tile halo metadata of one level (uploads; device pointers appended to `owned`).
 int build_umma_level_meta(const int* rowptr, const int* colidx, const float* val, int V, DevLevel* out,
                           std::vector<void*>* owned);
+// Tiles of 128 consecutive entries of `rows` (ascending vertex ids of one level) as a TileSet (trimmed blobs).
+int build_index_tiles(const std::vector<int>& rows, const int* rowptr, const int* colidx, const float* val, int V,
+                      TileSet* ts, std::vector<void*>* owned);
 bool umma_conv_supported(const DevLevel& g, int fin, int fout);
 size_t umma_wpack_bytes(int fin, int fout);
 int launch_umma_pack_weights(const float* W /*[fout, fin*3] ref layout*/, int fin, int fout, void* wpack, cudaStream_t s);
@@ -235,12 +261,26 @@ int launch_absmax_scale(const float* x, long long n, float* scale_out, cudaStrea
 bool umma_dw_supported(const DevLevel& g, int fin, int fout);
 int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout, const float* dz,
                    const float* a_scale, float* dw_ref, int* status, int sm_count, cudaStream_t s);
+// The same sum through the basis of the gradient (L~ symmetric): dW[o, f*3+k] += sum_rows T_k(dz)[row,o] * x[row,f], with
+// t1_dz = L~ dz [rows, fout] given for EVERY row (the backward-data pass leaves it behind): no 2-hop halo, no T1 on chip
+bool umma_dw_swapped_supported(const DevLevel& g, int fin, int fout);
+int launch_umma_dw_swapped(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, int fout,
+                           const float* dz, const float* t1_dz, const float* a_scale, float* dw_ref, int* status,
+                           int sm_count, cudaStream_t s);
 // T1 = L~ x for all rows of a level (tile-staged gather), t1 [batch*V, fin] fp32
 int launch_cheb_t1(const DevLevel& g, const float* x, int in_unpool, int batch, int fin, float* t1, cudaStream_t s,
                    const TileSet* tiles = nullptr);
 // K-blocks of the combined weights of the isolated rows: B[n][f] = W[n][3f] + c W[n][3f+1] + (2c^2 - 1) W[n][3f+2]
 // (W in the reference layout [fout, fin*3]); same image as launch_umma_pack_plain(N = fout, K = fin)
 int launch_umma_pack_iso(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s);
+// Backward-data weights: the forward conv run on dz with W'[f][o*3+k] = W[o][f*3+k] gives dX (L~ is symmetric); images
+// for a layer with Fin' = fout, Fout' = fin: umma_wpack_bytes(fout, fin) / umma_plain_pack_bytes(fin, fout) bytes
+int launch_umma_pack_weights_t(const float* W /*[fout, fin*3]*/, int fin, int fout, void* wpack, cudaStream_t s);
+int launch_umma_pack_iso_t(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s);
 int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
+// out[ro, :] = sum over the logical rows r of physical row ro (r = ro, or 2 ro and 2 ro + 1 under the virtual unpool)
+// of  dxl[r, :] + resample^T(g_res[r, :])   (g_res may be null)
+int launch_dx_finish(const float* dxl, int rows, int F, const float* g_res, int res_Fout, const InterpTable* it,
+                     int out_pairsum, float* out, cudaStream_t s);
 
 }  // namespace p2m

@@ -4,9 +4,10 @@
     import pose2mesh_release_b200.install as p2m; p2m.install()
     import core.base                        # Trainer / Tester now build the B200 MeshNet
 
-``install()`` rebinds ``models.meshnet.Pose2Mesh`` / ``get_model`` and
-``models.backbones.cheby_graph_conv.graph_conv_cheby`` and swaps ``graph_utils.build_coarse_graphs``
-for the native-matching builder; ``uninstall()`` restores the originals.  Nothing in the reference
+``install()`` rebinds ``models.meshnet.Pose2Mesh`` / ``get_model``,
+``models.backbones.cheby_graph_conv.graph_conv_cheby`` and ``models.posenet.LinearModel`` / ``get_model`` (the
+PoseNet in front of MeshNet: the reference's own ``FlatPose2Mesh`` then runs both halves natively in eval mode) and
+swaps ``graph_utils.build_coarse_graphs`` for the native-matching builder; ``uninstall()`` restores the originals.  Nothing in the reference
 tree is modified on disk.
 """
 from __future__ import annotations
@@ -39,7 +40,12 @@ def install(replace_graph_builder: bool = True):
     from . import cheby_graph_conv as my_conv
     from . import graph as my_graph
     from . import meshnet as my_meshnet
+    from . import posenet as my_posenet
 
+    ref_posenet = importlib.import_module("models.posenet")
+    _saved.setdefault("posenet", (ref_posenet.LinearModel, ref_posenet.get_model))
+    ref_posenet.LinearModel = my_posenet.LinearModel
+    ref_posenet.get_model = my_posenet.get_model
     ref_meshnet = importlib.import_module("models.meshnet")
     ref_conv = importlib.import_module("models.backbones.cheby_graph_conv")
     _saved.setdefault("meshnet", (ref_meshnet.Pose2Mesh, ref_meshnet.get_model, ref_meshnet.graph_conv_cheby))
@@ -63,6 +69,9 @@ def uninstall():
     if "meshnet" in _saved:
         ref_meshnet = importlib.import_module("models.meshnet")
         ref_meshnet.Pose2Mesh, ref_meshnet.get_model, ref_meshnet.graph_conv_cheby = _saved.pop("meshnet")
+    if "posenet" in _saved:
+        ref_posenet = importlib.import_module("models.posenet")
+        ref_posenet.LinearModel, ref_posenet.get_model = _saved.pop("posenet")
     if "conv" in _saved:
         importlib.import_module("models.backbones.cheby_graph_conv").graph_conv_cheby = _saved.pop("conv")
     if "graph" in _saved:

@@ -98,7 +98,8 @@ class BakedHierarchy:
         _lib.check(_lib.load().p2m_model_set_profiling(self.handle(device_index), int(enable)), "set_profiling")
 
     def set_debug(self, device_index: int, split_t1: Optional[bool] = None, fuse_head: Optional[bool] = None,
-                  elide_padding: Optional[int] = None):
+                  elide_padding: Optional[int] = None, dedup_padding: Optional[bool] = None,
+                  dw_swap: Optional[bool] = None):
         """Ablation switches of the tcgen05 path: separate T1 pass (default on), fused 64->3 head in eval (default
         on), isolated padding vertices through a plain GEMM with combined weights (0 off, 1 = default: levels with
         >= 40 % isolated rows, 2 = every level that has the tile families)."""
@@ -109,6 +110,10 @@ class BakedHierarchy:
             _lib.check(lib.p2m_debug_set_fuse_head(h, int(fuse_head)), "set_fuse_head")
         if elide_padding is not None:
             _lib.check(lib.p2m_debug_set_elide_padding(h, int(elide_padding)), "set_elide_padding")
+        if dw_swap is not None:  # backward: dW from the basis of the gradient (default on) or of the layer input
+            _lib.check(lib.p2m_debug_set_dw_swap(h, int(dw_swap)), "set_dw_swap")
+        if dedup_padding is not None:  # eval: one representative per class of identical isolated rows (default on)
+            _lib.check(lib.p2m_debug_set_dedup_padding(h, int(dedup_padding)), "set_dedup_padding")
 
     def layer_info(self, device_index: int):
         lib = _lib.load()

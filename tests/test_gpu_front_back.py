@@ -1,0 +1,139 @@
+"""GPU parity of the steps either side of MeshNet: PoseNet + the FlatPose2Mesh concat,
+the demo's input normalisation and the joint regression, against the CPU oracle (oracle/demo_oracle.py) and the
+outputs of the unmodified reference functions (tests/golden/demo_pipeline.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import graph_from_fixture, load_npz, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _posenet_with_golden_weights():
+    from oracle import demo_oracle as do
+    from oracle import meshnet_oracle as mo
+    from pose2mesh_release_b200 import posenet
+
+    torch.manual_seed(123)
+    sd = do.posenet_init_state_dict(17)
+    mo.randomize_bn_({("bn." + k): v for k, v in sd.items() if "batch_norm" in k}, seed=11)
+    net = posenet.get_model(17, hid_dim=4096, num_layer=2, p_dropout=0.5)
+    net.load_state_dict(sd)
+    return net.to(dev()).eval(), sd
+
+
+def test_posenet_eval_matches_reference_golden_and_oracle():
+    from oracle import demo_oracle as do
+
+    z = load_npz("demo_pipeline.npz")
+    net, sd = _posenet_with_golden_weights()
+    pose2d = torch.from_numpy(z["pose2d"])
+    with torch.no_grad():
+        pose3d, comb = net.forward_native(pose2d.to(dev()), with_combine=True)
+        assert rel_err(net(pose2d.to(dev()).reshape(8, -1)), torch.from_numpy(z["pose3d"])) < 1e-5   # nn.Module path
+    assert pose3d.shape == (8, 51) and comb.shape == (8, 17, 5)
+    assert rel_err(pose3d, torch.from_numpy(z["pose3d"])) < 1e-5            # the unmodified reference's PoseNet
+    np.testing.assert_allclose(comb.cpu().numpy(), z["pose_combine"], rtol=1e-5, atol=1e-7)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(300, 34, generator=g)                                    # a ragged batch (GEMM tile tails)
+    with torch.no_grad():
+        got = net.forward_native(x.to(dev()))
+        ref = do.posenet_forward(sd, x)
+    assert rel_err(got, ref) < 1e-5
+
+
+def test_flat_pose2mesh_matches_oracle_pipeline():
+    """FlatPose2Mesh.forward (pose2mesh_net.py:16-22) end to end: PoseNet -> concat -> MeshNet, eval mode."""
+    from oracle import demo_oracle as do
+    from oracle import meshnet_oracle as mo
+    from pose2mesh_release_b200 import pose2mesh_net
+
+    mats, zg = graph_from_fixture("smpl_small")
+    torch.manual_seed(123)
+    flat = pose2mesh_net.get_model(17, mats)
+    sd = {k: v.detach().clone() for k, v in flat.state_dict().items()}
+    mo.randomize_bn_({("bn." + k): v for k, v in sd.items() if "batch_norm" in k or ".bn." in k}, seed=3)
+    flat.load_state_dict(sd)
+    flat = flat.to(dev()).eval()
+    pose2d = torch.randn(5, 17, 2, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        mesh, pose3d = flat(pose2d.to(dev()))
+    sd_p = {k[len("pose_lifter."):]: v for k, v in sd.items() if k.startswith("pose_lifter.")}
+    sd_m = {k[len("pose2mesh."):]: v for k, v in sd.items() if k.startswith("pose2mesh.")}
+    with torch.no_grad():
+        p3 = do.posenet_forward(sd_p, pose2d.reshape(5, -1))
+        yo = mo.forward(sd_m, mo.laplacians_to_torch(mats), do.flat_pose2mesh_input(pose2d, p3), training=False)
+    assert pose3d.shape == (5, 17, 3) and rel_err(pose3d.reshape(5, -1), p3) < 1e-5
+    assert rel_err(mesh, yo) < 1e-4
+    # the callers' tail (base.py:130-131): gather + joint regression
+    perm_rev = np.asarray(zg["perm_reverse"])
+    jr = torch.rand(17, 1200, generator=torch.Generator().manual_seed(6))
+    jr = jr / jr.sum(1, keepdim=True)
+    verts, joints, _ = flat.predict_vertices_and_joints(pose2d.to(dev()), perm_rev, 1200, jr)
+    vo, jo = do.regress_joints(yo, perm_rev, 1200, jr)
+    assert rel_err(verts, vo) < 1e-4 and rel_err(joints, jo) < 1e-4
+
+
+def test_normalize_pose2d_matches_reference_golden_and_oracle():
+    from oracle import demo_oracle as do
+    from pose2mesh_release_b200 import postprocess
+
+    z = load_npz("demo_pipeline.npz")
+    ji = torch.from_numpy(z["joint_input"]).to(dev())                        # int64, like demo/h36m_joint_input.npy
+    got = postprocess.normalize_pose2d(ji)
+    np.testing.assert_allclose(got.cpu().numpy()[0], z["joint_img"][0], atol=2e-6)
+    g = np.random.default_rng(2)
+    poses = (g.uniform(0, 1, (64, 17, 2)) * np.array([640.0, 480.0]) + g.uniform(0, 300, (64, 1, 2))).astype(np.float32)
+    got = postprocess.normalize_pose2d(torch.from_numpy(poses).to(dev())).cpu().numpy()
+    ref = np.stack([do.normalize_pose2d(p.astype(np.float64)) for p in poses])
+    np.testing.assert_allclose(got, ref, atol=2e-5)
+
+
+def test_regress_joints_matches_matmul():
+    from pose2mesh_release_b200 import postprocess
+
+    g = torch.Generator().manual_seed(8)
+    verts = torch.randn(7, 6890, 3, generator=g)
+    jr = torch.rand(17, 6890, generator=g)
+    got = postprocess.regress_joints(verts.to(dev()), jr.to(dev()))
+    assert rel_err(got, torch.matmul(jr.double(), verts.double())) < 1e-5
+
+
+def test_mesh_losses_match_reference_golden_and_oracle():
+    """Row f3: NormalVectorLoss / EdgeLengthLoss / CoordLoss (lib/core/loss.py) forward + backward on the GPU."""
+    from oracle import loss_oracle as lo
+    from pose2mesh_release_b200 import loss as L
+
+    z = load_npz("mesh_losses.npz")
+    face = z["face"]
+    out = torch.from_numpy(z["out"]).to(dev()).requires_grad_(True)
+    gt, valid = torch.from_numpy(z["gt"]).to(dev()), torch.from_numpy(z["valid"]).to(dev())
+    c_loss, n_loss, e_loss, _, _ = L.get_loss(face)
+    ln, le, lc = n_loss(out, gt), e_loss(out, gt), c_loss(out, gt, valid)
+    assert abs(ln.item() - float(z["normal"])) < 2e-6
+    assert abs(le.item() - float(z["edge"])) < 2e-6
+    assert abs(lc.item() - float(z["coord"])) < 2e-6
+    w = z["weights"]
+    (float(w[0]) * ln + float(w[1]) * le + float(w[2]) * lc).backward()
+    ref = torch.from_numpy(z["grad"])
+    assert float((out.grad.cpu() - ref).abs().max() / ref.abs().max()) < 1e-4
+    # SMPL-size faces, both face losses from one pass, against the oracle
+    from pose2mesh_release_b200 import graph as pg
+
+    face = pg.synthetic_sphere_faces(6890, 2)
+    g = torch.Generator().manual_seed(3)
+    gt = torch.randn(4, 6890, 3, generator=g)
+    out = (gt + 0.1 * torch.randn(4, 6890, 3, generator=g))
+    og = out.clone().to(dev()).requires_grad_(True)
+    ln, le = L.MeshLosses(face)(og, gt.to(dev()))
+    (ln + 2 * le).backward()
+    oc = out.clone().requires_grad_(True)
+    rn, re = lo.normal_vector_loss(oc, gt, face), lo.edge_length_loss(oc, gt, face)
+    (rn + 2 * re).backward()
+    assert abs(ln.item() - rn.item()) < 1e-5 and abs(le.item() - re.item()) < 1e-5
+    assert float((og.grad.cpu() - oc.grad).abs().max() / oc.grad.abs().max()) < 1e-3

@@ -273,12 +273,24 @@ def test_full_size_smpl_eval_against_oracle(precision):
                 model.eval()
                 res[mode] = (y_eval, y_train)
             assert hier.kernel_status(d) == 0
+            # duplicate elimination among the isolated rows (eval, default on) against computing every row: ALL
+            # 12288 rows of every mesh, i.e. including the rows that were filled from their class representative
+            hier.set_debug(d, elide_padding=1, dedup_padding=False)
+            with torch.no_grad():
+                model.eval()
+                y_all_rows = model(x.to(dev()))
+            hier.set_debug(d, dedup_padding=True)
+            assert per_mesh_rel_err(y_all_rows, y) < 2e-5
+            assert per_mesh_rel_err(y_all_rows[pick], yo) < TOL_Y
+            with torch.no_grad():
+                verts = model.forward_vertices(x.to(dev()), perm_rev, n)      # computes no isolated row at all
+            assert torch.equal(verts, y[:, real.to(dev())])
             assert per_mesh_rel_err(res[0][0], y) < 2e-5
             assert per_mesh_rel_err(res[2][0], y) < 2e-5
             assert per_mesh_rel_err(res[2][0][pick], yo) < TOL_Y
             assert per_mesh_rel_err(res[2][1], res[0][1]) < 2e-5
         finally:
-            hier.set_debug(d, elide_padding=1)
+            hier.set_debug(d, elide_padding=1, dedup_padding=True)
 
 
 @pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
@@ -438,3 +450,37 @@ def test_tcgen05_conv_backward_matches_oracle(case):
     mo.cheb_conv(xo, lap, wo, bias).backward(gy)
     assert rel_err(xg.grad, xo.grad) < 1e-5
     assert rel_err(cl.weight.grad, wo.grad) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
+def test_backward_variants_agree(name):
+    """The two ways of forming the tensor-core weight gradient — from the basis of the gradient (default: re-uses the
+    backward-data pass's L~dz) or from the basis of the layer input (rebuilt on chip) — and the SIMT (fp32) backward
+    agree on every parameter gradient and on dx."""
+    n, seed, levels, mano = CASES[name]
+    grads = {}
+    x = torch.randn(4, 21 if mano else 17, 5, generator=torch.Generator().manual_seed(11))
+    for tag, prec, swap in (("swap", "fp16x3", True), ("input-basis", "fp16x3", False), ("simt", "fp32", True)):
+        model, mats, _ = make_model(name, prec)
+        for k, v in model.state_dict().items():        # open ReLUs: no activation can flip between the variants
+            if k.startswith("bn.") and k.endswith(".bias"):
+                v.fill_(6.0)
+        model._hier.set_debug(torch.cuda.current_device(), dw_swap=swap)
+        try:
+            model.train()
+            xg = x.to(dev()).requires_grad_(True)
+            tgt = torch.randn(4, model.num_vertices, 3, generator=torch.Generator().manual_seed(12)).to(dev())
+            (model(xg) - tgt).abs().mean().backward()
+            assert model._hier.kernel_status(torch.cuda.current_device()) == 0
+            grads[tag] = ({k: p.grad.detach().clone() for k, p in model.named_parameters()}, xg.grad.clone())
+        finally:
+            model._hier.set_debug(torch.cuda.current_device(), dw_swap=True)
+    ref_p, ref_x = grads["simt"]
+    scale = max(float(g.abs().max()) for g in ref_p.values())
+    for tag in ("swap", "input-basis"):
+        got_p, got_x = grads[tag]
+        ok, info = grad_close(got_x, ref_x)
+        assert ok, (tag, "dx", info)
+        for k in ref_p:
+            ok, info = grad_close(got_p[k], ref_p[k], scale=1e-3 * scale)
+            assert ok, (tag, k, info)

@@ -65,6 +65,9 @@ def test_flat_pose2mesh_builds_the_b200_meshnet(reference):
     pose2mesh_net = importlib.import_module("models.pose2mesh_net")
     flat = pose2mesh_net.get_model(17, [m.copy() for m in mats])
     assert isinstance(flat.pose2mesh, p2m.Pose2Mesh)
+    from pose2mesh_release_b200 import posenet as my_posenet
+
+    assert isinstance(flat.pose_lifter, my_posenet.LinearModel)               # the front half is rebound as well
     got = sorted(k[len("pose2mesh."):] for k in flat.state_dict() if k.startswith("pose2mesh."))
     assert got == ref_keys
     flat.pose2mesh.load_state_dict(ref_model.state_dict())                    # reference checkpoints load unchanged
@@ -85,3 +88,25 @@ def test_precision_env_override(monkeypatch):
     monkeypatch.setenv("P2M_PRECISION", "bf16")
     with pytest.raises(RuntimeError, match="P2M_PRECISION"):
         _lib.default_precision()
+
+
+def test_posenet_mirror_has_the_reference_state_dict(reference):
+    """models.posenet.LinearModel (lib/models/posenet.py:41-72) and the B200 mirror: same keys, shapes and — under the
+    same seed — the same initial values, so PoseNet checkpoints load unchanged."""
+    import importlib
+
+    from pose2mesh_release_b200 import pose2mesh_net as my_flat
+    from pose2mesh_release_b200 import posenet as my_posenet
+
+    ref_posenet = importlib.import_module("models.posenet")
+    torch.manual_seed(5)
+    ref = ref_posenet.get_model(17, hid_dim=64, num_layer=2, p_dropout=0.5, pretrained=False)
+    torch.manual_seed(5)
+    mine = my_posenet.get_model(17, hid_dim=64, num_layer=2, p_dropout=0.5, pretrained=False)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert rs[k].shape == ms[k].shape and torch.equal(rs[k], ms[k]), k
+    mats, _ = graph_from_fixture("smpl_small")
+    flat = my_flat.get_model(17, [m.copy() for m in mats])
+    assert {k.split(".")[0] for k in flat.state_dict()} == {"pose_lifter", "pose2mesh"}   # pose2mesh_net.py:13-14

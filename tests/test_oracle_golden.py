@@ -177,3 +177,44 @@ def test_demo_oracle_matches_reference_golden():
     np.testing.assert_allclose(pose3d.numpy(), z["pose3d"], rtol=1e-5, atol=1e-6)
     comb = do.flat_pose2mesh_input(torch.from_numpy(z["pose2d"]), pose3d)
     np.testing.assert_allclose(comb.numpy(), z["pose_combine"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
+def test_children_of_padding_vertices_are_padding_vertices(name):
+    """What the eval-mode duplicate elimination among the isolated rows rests on (DevLevel::rep_tiles): in the
+    reference's binary-tree reorder (lib/coarsening.py:214-258) fake vertices are added bottom-up, so both children
+    (rows 2p, 2p+1 of the next finer level) of an isolated row p are isolated too, with the level's common diagonal."""
+    mats, _ = graph_from_fixture(name)
+    mesh_levels = mats[:-1]                       # the joint graph is last
+
+    def isolated(m):
+        c = m.tocsr()
+        deg = np.diff(c.indptr)
+        return (deg == 1) & (c.indices[np.minimum(c.indptr[:-1], c.nnz - 1)] == np.arange(c.shape[0]))
+
+    iso = [isolated(m) for m in mesh_levels]
+    checked = 0
+    for k in range(len(iso) - 1):
+        if mesh_levels[k].shape[0] != 2 * mesh_levels[k + 1].shape[0]:
+            continue
+        parents = np.nonzero(iso[k + 1])[0]
+        assert iso[k][2 * parents].all() and iso[k][2 * parents + 1].all(), k
+        checked += len(parents)
+    assert checked > 0
+
+
+def test_loss_oracle_matches_reference_golden():
+    """lib/core/loss.py:10-23,62-114 restated in oracle/loss_oracle.py vs the unmodified reference classes
+    (tests/golden/mesh_losses.npz): the three losses and the gradient of their weighted sum."""
+    from oracle import loss_oracle as lo
+
+    z = load_npz("mesh_losses.npz")
+    out = torch.from_numpy(z["out"]).requires_grad_(True)
+    gt, valid, face = torch.from_numpy(z["gt"]), torch.from_numpy(z["valid"]), z["face"].astype(np.int64)
+    ln, le, lc = lo.normal_vector_loss(out, gt, face), lo.edge_length_loss(out, gt, face), lo.coord_loss(out, gt, valid)
+    assert abs(ln.item() - float(z["normal"])) < 1e-6
+    assert abs(le.item() - float(z["edge"])) < 1e-6
+    assert abs(lc.item() - float(z["coord"])) < 1e-6
+    w = z["weights"]
+    (w[0] * ln + w[1] * le + w[2] * lc).backward()
+    np.testing.assert_allclose(out.grad.numpy(), z["grad"], rtol=1e-4, atol=1e-8)
