@@ -205,31 +205,41 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.z = fmaf(w, x.z, acc.z);
   acc.w = fmaf(w, x.w, acc.w);
 }
-// One CSR row with four entries in flight: the four (slot, value) pairs are fetched first, then the four
-// 16-byte row pieces, then the FMAs on two accumulators — the row's dependent chain is ~2 shared-memory round
-// trips per four entries instead of two per entry (rows have <= 14 entries).
+// One CSR row, gathered by the 8 lanes that share it (lane & 7 = 16-byte piece of the 128-byte row chunk).  The
+// (slot offset, value) entries are fetched ONCE per row: lane q loads entry e + q (one 64-byte access per row instead
+// of eight broadcast loads per entry) and the group passes them round with width-8 shuffles — the entry loads were
+// 10 % of the kernels' shared-memory wavefronts, shuffles cost none.  Up to four row pieces are in flight per step,
+// accumulated on two registers sets (rows have <= 14 entries).  All 8 lanes of a group see the same (e, e1).
 __device__ __forceinline__ float4 gather_row4(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
+  const uint32_t lane = threadIdx.x & 31u, q = lane & 7u;
+  const unsigned gmask = 0xFFu << (lane & 24u);
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-  for (; e + 3 < e1; e += 4) {
-    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8), a2 = lds_u2(ent + e * 8 + 16),
-                a3 = lds_u2(ent + e * 8 + 24);
-    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x), x2 = lds_f4(rows_q + a2.x),
-                 x3 = lds_f4(rows_q + a3.x);
-    fma4(acc0, __uint_as_float(a0.y), x0);
-    fma4(acc1, __uint_as_float(a1.y), x1);
-    fma4(acc0, __uint_as_float(a2.y), x2);
-    fma4(acc1, __uint_as_float(a3.y), x3);
-  }
-  if (e + 1 < e1) {
-    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8);
-    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x);
-    fma4(acc0, __uint_as_float(a0.y), x0);
-    fma4(acc1, __uint_as_float(a1.y), x1);
-    e += 2;
-  }
-  if (e < e1) {
-    const uint2 a0 = lds_u2(ent + e * 8);
-    fma4(acc0, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
+  while (e < e1) {
+    const uint32_t n = min(e1 - e, 8u);
+    uint2 mine = make_uint2(0u, 0u);
+    if (q < n) mine = lds_u2(ent + (e + q) * 8);
+    uint32_t j = 0;
+    for (; j + 3 < n; j += 4) {
+      const uint32_t o0 = __shfl_sync(gmask, mine.x, j, 8), o1 = __shfl_sync(gmask, mine.x, j + 1, 8),
+                     o2 = __shfl_sync(gmask, mine.x, j + 2, 8), o3 = __shfl_sync(gmask, mine.x, j + 3, 8);
+      const float4 x0 = lds_f4(rows_q + o0), x1 = lds_f4(rows_q + o1), x2 = lds_f4(rows_q + o2), x3 = lds_f4(rows_q + o3);
+      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j, 8)), x0);
+      fma4(acc1, __uint_as_float(__shfl_sync(gmask, mine.y, j + 1, 8)), x1);
+      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j + 2, 8)), x2);
+      fma4(acc1, __uint_as_float(__shfl_sync(gmask, mine.y, j + 3, 8)), x3);
+    }
+    if (j + 1 < n) {
+      const uint32_t o0 = __shfl_sync(gmask, mine.x, j, 8), o1 = __shfl_sync(gmask, mine.x, j + 1, 8);
+      const float4 x0 = lds_f4(rows_q + o0), x1 = lds_f4(rows_q + o1);
+      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j, 8)), x0);
+      fma4(acc1, __uint_as_float(__shfl_sync(gmask, mine.y, j + 1, 8)), x1);
+      j += 2;
+    }
+    if (j < n) {
+      const uint32_t o0 = __shfl_sync(gmask, mine.x, j, 8);
+      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j, 8)), lds_f4(rows_q + o0));
+    }
+    e += n;
   }
   return make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
 }
@@ -799,14 +809,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           split4(v, hi, lo);
           const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
           // the four consecutive rows of a warp share (row & 4), i.e. the 64-byte half their hi parts go to: odd row
-          // groups store lo first, so that every store instruction of the warp covers both halves (no replays)
-          if (rg & 1) {
-            sts_u2(a_lo, lo);
-            sts_u2(a_hi, hi);
-          } else {
-            sts_u2(a_hi, hi);
-            sts_u2(a_lo, lo);
-          }
+          // groups store lo first (selects, see emit()), so that both rows of a half-warp cover different bank halves
+          const bool odd = (rg & 1) != 0;
+          sts_u2(odd ? a_lo : a_hi, odd ? lo : hi);
+          sts_u2(odd ? a_hi : a_lo, odd ? hi : lo);
         }
         fence_async_proxy();
         __syncwarp();
@@ -850,13 +856,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           }
           split4(v, hi, lo);
           const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
-          if (rg & 1) {
-            sts_u2(a_lo, lo);
-            sts_u2(a_hi, hi);
-          } else {
-            sts_u2(a_hi, hi);
-            sts_u2(a_lo, lo);
-          }
+          // 64-bit shared stores are served per HALF-warp (two rows here).  Odd row groups store lo first — by
+          // selects, not branches: a predicated store would leave each half-warp's wavefront half empty — and the
+          // row order pairs rows so that the two 64-byte pieces of a half-warp fall into different bank halves
+          const bool odd = (rg & 1) != 0;
+          sts_u2(odd ? a_lo : a_hi, odd ? lo : hi);
+          sts_u2(odd ? a_hi : a_lo, odd ? hi : lo);
         }
         if (NS < 3) {
           fence_async_proxy();
@@ -1170,7 +1175,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
           const int i = ps * 64 + rg;
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const int col = q * 4 + 32 * jj;  // channel inside this launch's 128-channel slice
+            // odd row groups take the 32-channel pieces in the order 1,0,3,2: the two rows of a half-warp then store
+            // into different 64-byte bank halves (their swizzle bits agree: consecutive rows)
+            const int col = q * 4 + 32 * (jj ^ (rg & 1));  // channel inside this launch's 128-channel slice
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n_rows && col < p.m_cols) {
               const long long rr = p.g_unpool ? ((r_base + i) >> 1) : (r_base + i);
@@ -1182,7 +1189,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
             uint2 hi, lo;
             split4(v, hi, lo);
             const uint32_t off = (uint32_t)(col >> 6) * A_BLOCK_BYTES + sw128_off(i, (col & 63) >> 3) + ((col >> 2) & 1) * 8;
-            sts_u2(g_a + off, hi);
+            sts_u2(g_a + off, hi);  // (rows i = ps*64 + rg: 8 lanes x 8 B = 64 B per row and store, hi and lo blocks apart)
             sts_u2(g_a + 2 * A_BLOCK_BYTES + off, lo);
           }
         }
@@ -1234,8 +1241,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
             const uint32_t i = ps ? row1 : row0;
             uint2 hi, lo;
             split4(tv[k][ps], hi, lo);
-            sts_u2(blk + sw128_off(i, q >> 1), hi);
-            sts_u2(blk + sw128_off(i, 4 + (q >> 1)), lo);
+            const uint32_t a_hi = blk + sw128_off(i, q >> 1), a_lo = blk + sw128_off(i, 4 + (q >> 1));
+            const bool odd = (rg & 1) != 0;  // see emit() of the conv kernel
+            sts_u2(odd ? a_lo : a_hi, odd ? lo : hi);
+            sts_u2(odd ? a_hi : a_lo, odd ? hi : lo);
           }
         }
         fence_async_proxy();
@@ -1514,10 +1523,12 @@ int launch_n(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_c
 namespace {
 // The producers store a tile row's fp16 hi part into one 64-byte half of its 128-byte A-block row and the lo part
 // into the other; which half is which follows the row's swizzle bit (row & 4).  A warp stores four rows per
-// instruction (row groups 4w .. 4w+3 of the order below, odd groups lo first), so an instruction is free of bank
-// replays iff positions (0, 2) of an aligned group of four hold rows of different half classes, and so do (1, 3).
-// Re-deal a length-sorted order accordingly: two rows of each class per group, taken in sorted order (a group's rows
-// still have similar lengths).  Pure re-ordering of which thread produces which row: results are unchanged.
+// instruction (row groups 4w .. 4w+3 of the order below, odd groups lo first) and 64-bit shared stores are served per
+// half-warp, i.e. per PAIR of rows (positions 0,1 and 2,3 of an aligned group of four): a pair is free of bank
+// replays iff its two 64-byte pieces fall into different halves — with the odd group storing the other part first,
+// iff both rows of the pair have the SAME half class.  Re-deal a length-sorted order accordingly: [c0 c0 c1 c1] per
+// group, taken in sorted order (a group's rows still have similar lengths).  Pure re-ordering of which thread
+// produces which row: results are unchanged.
 void balance_store_halves(std::vector<unsigned short>* ord) {
   std::vector<unsigned short> q0, q1;
   for (unsigned short r : *ord) ((r & 4) ? q1 : q0).push_back(r);

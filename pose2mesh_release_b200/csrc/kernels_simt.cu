@@ -998,45 +998,65 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
   float m2 = (float)(sums[F + f] / (double)rows);
   g_z[idx] = gamma[f] * invstd[f] * (g - m1 - zh * m2);
 }
+// BN + ReLU backward, pass 2, as a per-channel affine map:  g_z = a g' + b z + c  with
+//   a = gamma invstd,  b = -a invstd m2,  c = -a m1 + a invstd m2 mean,   m1 = s1 / rows, m2 = s2 / rows
+// (g_z = gamma invstd (g' - m1 - zhat m2), zhat = (z - mean) invstd), g' = g_a masked by the forward's own
+// activation test fma(z, scale, shift) > 0.  k_bn_bwd_coef builds coef[5][F] = a | b | c | scale | shift once per
+// layer; the streaming kernel then needs five 16-byte coefficient loads per four channels and no fp64.
+__global__ void k_bn_bwd_coef(const double* __restrict__ sums, long long rows, int F, const float* __restrict__ gamma,
+                              const float* __restrict__ scale, const float* __restrict__ shift,
+                              const float* __restrict__ mean, const float* __restrict__ invstd,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  dbeta[f] = (float)sums[f];
+  dgamma[f] = (float)sums[F + f];
+  const float m1 = (float)(sums[f] / (double)rows), m2 = (float)(sums[F + f] / (double)rows);
+  const float a = gamma[f] * invstd[f];
+  coef[f] = a;
+  coef[F + f] = -a * invstd[f] * m2;
+  coef[2 * F + f] = -a * m1 + a * invstd[f] * m2 * mean[f];
+  coef[3 * F + f] = scale[f];
+  coef[4 * F + f] = shift[f];
+}
 // four channels per thread; optionally folds max|g_z| into *amax (bits of a non-negative float, atomicMax): the
 // power-of-two scale of the tensor-core backward GEMMs then needs no pass of its own
 __global__ void __launch_bounds__(256) k_bn_bwd_apply4(const float4* __restrict__ z, const float4* __restrict__ g_a,
-                                                       long long n4, int F4, long long rows,
-                                                       const float* __restrict__ gamma, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, const float* __restrict__ mean,
-                                                       const float* __restrict__ invstd, int relu,
-                                                       const double* __restrict__ sums, float* __restrict__ dgamma,
-                                                       float* __restrict__ dbeta, float4* __restrict__ g_z,
-                                                       unsigned int* __restrict__ amax) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int F = 4 * F4;
-  if (idx < F) {
-    dbeta[idx] = (float)sums[idx];
-    dgamma[idx] = (float)sums[F + idx];
-  }
+                                                       long long n4, int F4, int relu, const float4* __restrict__ coef,
+                                                       float4* __restrict__ g_z, unsigned int* __restrict__ amax) {
+  // grid-stride: a few CTAs per SM, ONE atomicMax per CTA (per-warp atomics on a single address serialise in L2 and
+  // cost more than the whole streaming pass)
   float m = 0.f;
-  if (idx < n4) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n4;
+       idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % F4);
     const float4 zv = z[idx];
     float4 g = g_a[idx];
-    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-    float gg[4] = {g.x, g.y, g.z, g.w};
-    const double inv_rows = 1.0 / (double)rows;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int f = 4 * c + e;
-      const float zh = (zz[e] - mean[f]) * invstd[f];
-      if (relu && !(fmaf(zz[e], scale[f], shift[f]) > 0.f)) gg[e] = 0.f;  // exactly the forward's activation test
-      const float m1 = (float)(sums[f] * inv_rows);
-      const float m2 = (float)(sums[F + f] * inv_rows);
-      gg[e] = gamma[f] * invstd[f] * (gg[e] - m1 - zh * m2);
-      m = fmaxf(m, fabsf(gg[e]));
+    const float4 ca = __ldg(coef + c), cb = __ldg(coef + F4 + c), cc = __ldg(coef + 2 * F4 + c);
+    if (relu) {
+      const float4 sc = __ldg(coef + 3 * F4 + c), sh = __ldg(coef + 4 * F4 + c);
+      if (!(fmaf(zv.x, sc.x, sh.x) > 0.f)) g.x = 0.f;  // exactly the forward's activation test
+      if (!(fmaf(zv.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
+      if (!(fmaf(zv.z, sc.z, sh.z) > 0.f)) g.z = 0.f;
+      if (!(fmaf(zv.w, sc.w, sh.w) > 0.f)) g.w = 0.f;
     }
-    g_z[idx] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    float4 o;
+    o.x = fmaf(ca.x, g.x, fmaf(cb.x, zv.x, cc.x));
+    o.y = fmaf(ca.y, g.y, fmaf(cb.y, zv.y, cc.y));
+    o.z = fmaf(ca.z, g.z, fmaf(cb.z, zv.z, cc.z));
+    o.w = fmaf(ca.w, g.w, fmaf(cb.w, zv.w, cc.w));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+    g_z[idx] = o;
   }
   if (amax != nullptr) {
+    __shared__ float red[8];
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+      if (m > 0.f) atomicMax(amax, __float_as_uint(m));
+    }
   }
 }
 int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* scale,
@@ -1050,10 +1070,14 @@ int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const 
   if (F % 4 == 0 && al) {
     if (gz_scale_out) P2M_CUDA_OK(cudaMemsetAsync(gz_scale_out, 0, sizeof(float), s));
     const long long n4 = (long long)rows * (F / 4);
-    k_bn_bwd_apply4<<<cdiv(std::max<long long>(n4, F), 256), 256, 0, s>>>(
-        reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(g_a), n4, F / 4, rows, gamma, scale, shift,
-        mean, invstd, relu, sums, dgamma, dbeta, reinterpret_cast<float4*>(g_z),
-        reinterpret_cast<unsigned int*>(gz_scale_out));
+    float* coef = reinterpret_cast<float*>(sums + 2 * F);  // [5][F] floats behind the two fp64 sums
+    k_bn_bwd_coef<<<cdiv(F, 128), 128, 0, s>>>(sums, rows, F, gamma, scale, shift, mean, invstd, dgamma, dbeta, coef);
+    P2M_LAUNCH_OK();
+    const int grid = (int)std::min<long long>((n4 + 255) / 256, 148LL * 16);
+    k_bn_bwd_apply4<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(z),
+                                                  reinterpret_cast<const float4*>(g_a), n4, F / 4, relu,
+                                                  reinterpret_cast<const float4*>(coef), reinterpret_cast<float4*>(g_z),
+                                                  reinterpret_cast<unsigned int*>(gz_scale_out));
     P2M_LAUNCH_OK();
     if (gz_scale_out) {
       k_scale_from_absmax<<<1, 1, 0, s>>>(reinterpret_cast<unsigned int*>(gz_scale_out));

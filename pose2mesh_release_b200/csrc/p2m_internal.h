@@ -207,7 +207,8 @@ int launch_affine_act(const float* z, int rows, int F, const float* scale, const
 // written.  The ReLU mask is recomputed from z (block-end activations already include the residual).
 int launch_bn_relu_bwd(const float* z, const float* g_a, int rows, int F, const float* gamma, const float* scale,
                        const float* shift, const float* mean, const float* invstd, int relu,
-                       double* sums /*[2F] scratch*/, float* dgamma, float* dbeta, float* g_z, cudaStream_t s,
+                       double* sums /*scratch: 2F doubles + 5F floats, 16-byte aligned*/, float* dgamma, float* dbeta,
+                       float* g_z, cudaStream_t s,
                        float* gz_scale_out = nullptr /* optional device scalar: launch_absmax_scale(g_z) fused in */);
 int launch_col_sum(const float* g, int rows, int F, double* scratch /*[F]*/, float* out, cudaStream_t s);
 
