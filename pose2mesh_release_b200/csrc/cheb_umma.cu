@@ -205,41 +205,33 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.z = fmaf(w, x.z, acc.z);
   acc.w = fmaf(w, x.w, acc.w);
 }
-// One CSR row, gathered by the 8 lanes that share it (lane & 7 = 16-byte piece of the 128-byte row chunk).  The
-// (slot offset, value) entries are fetched ONCE per row: lane q loads entry e + q (one 64-byte access per row instead
-// of eight broadcast loads per entry) and the group passes them round with width-8 shuffles — the entry loads were
-// 10 % of the kernels' shared-memory wavefronts, shuffles cost none.  Up to four row pieces are in flight per step,
-// accumulated on two registers sets (rows have <= 14 entries).  All 8 lanes of a group see the same (e, e1).
+// One CSR row with four entries in flight: the four (slot, value) pairs are fetched first, then the four
+// 16-byte row pieces, then the FMAs on two accumulators — the row's dependent chain is ~2 shared-memory round
+// trips per four entries instead of two per entry (rows have <= 14 entries).  (Fetching each entry once per row and
+// passing it round the row's 8 lanes with width-8 shuffles was measured in round 2: 15 % SLOWER — shuffles run on
+// the same MIO/shared-memory pipe that bounds these kernels.)
 __device__ __forceinline__ float4 gather_row4(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
-  const uint32_t lane = threadIdx.x & 31u, q = lane & 7u;
-  const unsigned gmask = 0xFFu << (lane & 24u);
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-  while (e < e1) {
-    const uint32_t n = min(e1 - e, 8u);
-    uint2 mine = make_uint2(0u, 0u);
-    if (q < n) mine = lds_u2(ent + (e + q) * 8);
-    uint32_t j = 0;
-    for (; j + 3 < n; j += 4) {
-      const uint32_t o0 = __shfl_sync(gmask, mine.x, j, 8), o1 = __shfl_sync(gmask, mine.x, j + 1, 8),
-                     o2 = __shfl_sync(gmask, mine.x, j + 2, 8), o3 = __shfl_sync(gmask, mine.x, j + 3, 8);
-      const float4 x0 = lds_f4(rows_q + o0), x1 = lds_f4(rows_q + o1), x2 = lds_f4(rows_q + o2), x3 = lds_f4(rows_q + o3);
-      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j, 8)), x0);
-      fma4(acc1, __uint_as_float(__shfl_sync(gmask, mine.y, j + 1, 8)), x1);
-      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j + 2, 8)), x2);
-      fma4(acc1, __uint_as_float(__shfl_sync(gmask, mine.y, j + 3, 8)), x3);
-    }
-    if (j + 1 < n) {
-      const uint32_t o0 = __shfl_sync(gmask, mine.x, j, 8), o1 = __shfl_sync(gmask, mine.x, j + 1, 8);
-      const float4 x0 = lds_f4(rows_q + o0), x1 = lds_f4(rows_q + o1);
-      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j, 8)), x0);
-      fma4(acc1, __uint_as_float(__shfl_sync(gmask, mine.y, j + 1, 8)), x1);
-      j += 2;
-    }
-    if (j < n) {
-      const uint32_t o0 = __shfl_sync(gmask, mine.x, j, 8);
-      fma4(acc0, __uint_as_float(__shfl_sync(gmask, mine.y, j, 8)), lds_f4(rows_q + o0));
-    }
-    e += n;
+  for (; e + 3 < e1; e += 4) {
+    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8), a2 = lds_u2(ent + e * 8 + 16),
+                a3 = lds_u2(ent + e * 8 + 24);
+    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x), x2 = lds_f4(rows_q + a2.x),
+                 x3 = lds_f4(rows_q + a3.x);
+    fma4(acc0, __uint_as_float(a0.y), x0);
+    fma4(acc1, __uint_as_float(a1.y), x1);
+    fma4(acc0, __uint_as_float(a2.y), x2);
+    fma4(acc1, __uint_as_float(a3.y), x3);
+  }
+  if (e + 1 < e1) {
+    const uint2 a0 = lds_u2(ent + e * 8), a1 = lds_u2(ent + e * 8 + 8);
+    const float4 x0 = lds_f4(rows_q + a0.x), x1 = lds_f4(rows_q + a1.x);
+    fma4(acc0, __uint_as_float(a0.y), x0);
+    fma4(acc1, __uint_as_float(a1.y), x1);
+    e += 2;
+  }
+  if (e < e1) {
+    const uint2 a0 = lds_u2(ent + e * 8);
+    fma4(acc0, __uint_as_float(a0.y), lds_f4(rows_q + a0.x));
   }
   return make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
 }
@@ -950,6 +942,8 @@ struct DwParams {
   const float* t1;
   int g_unpool;
   int swap;
+  int tma;                 // T1 given, consecutive tiles, V % 128 == 0: the own rows of x and t1 arrive by one 2-D TMA box each
+  CUtensorMap tm_x, tm_t1;
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes) {
@@ -966,7 +960,7 @@ constexpr int DW_NS = 3;
 constexpr int DW_G_BYTES = 4 * A_BLOCK_BYTES;  // dz tile: (hi, lo) x two 64-channel groups
 
 template <int XS>
-__global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams p) {
+__global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_constant__ DwParams p) {
   constexpr uint32_t IDESC = make_idesc_f16(TILE_M, 64) | (1u << 15) | (1u << 16);  // A and B MN-major
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;                      // [DW_NS] T blocks
@@ -1001,7 +995,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
       mbar_init(smem_u32(b_t_empty + s), 1);
     }
     for (int s = 0; s < XS; ++s) {
-      mbar_init(smem_u32(b_x_full + s), N_XLOAD * 32);
+      mbar_init(smem_u32(b_x_full + s), N_XLOAD * 32 + 1);  // the loader threads' cp.async arrivals + one expect_tx / plain arrival
       mbar_init(smem_u32(b_x_empty + s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -1048,11 +1042,35 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
       const int h1 = hdr->h1;
       const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);
       const long long mesh_row0 = (long long)b * p.V;
+      if (it + 1 < my_tiles) {
+        // the producers read the NEXT tile's plain-side rows straight from global memory at the start of that tile:
+        // pull them into L2 now (consecutive tiles only; index-list tiles would need the next blob first)
+        const int tile2 = blockIdx.x + (it + 1) * gridDim.x;
+        const long long r2 = (long long)(tile2 / p.P) * p.V + (long long)(tile2 % p.P) * TILE_M;
+        const int lpr = (p.m_cols * 4 + 127) >> 7;  // 128-byte lines per row of this launch's channel slice
+        for (int j = lt; j < TILE_M * lpr; j += N_XLOAD * 32) {
+          const long long rr = r2 + j / lpr;
+          if (rr < (long long)(tile2 / p.P + 1) * p.V)
+            prefetch_l2(p.g + (p.g_unpool ? (rr >> 1) : rr) * p.fout_total + p.m_off + (j % lpr) * 32);
+        }
+      }
       for (int c = 0; c < n_chunk; ++c, ++g) {
         const int xs = g % XS;
         mbar_wait_relaxed(smem_u32(b_x_empty + xs), ((g / XS) & 1) ^ 1, abort_flag, p.status, 23);
         const uint32_t dst0 = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
         const float* src0 = p.x + (p.chunk0 + c) * FC + q * 4;
+        const uint32_t xbar = smem_u32(b_x_full + xs);
+        if (lt == 0) {
+          if (p.tma) {  // own rows of x and t1: one TMA box each, landing asynchronously
+            const int own0 = tile * TILE_M;  // V is a multiple of 128: tiles never straddle meshes
+            mbar_arrive_expect_tx(xbar, 2 * TILE_M * 128);
+            tma_load_2d(smem_u32(Xs + xs * xs_stage_floats), &p.tm_x, (p.chunk0 + c) * FC, own0, xbar);
+            tma_load_2d(smem_u32(T1s + xs * t1_stage_floats), &p.tm_t1, (p.chunk0 + c) * FC, own0, xbar);
+          } else {
+            mbar_arrive(xbar);
+          }
+        }
+        if (!p.tma)
         for (int i = rg; i < h2; i += 8) {
           const int v = halo[i];
           if (v >= 0) {
@@ -1066,7 +1084,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
         if (t1g) {  // ... plus the T1 rows of the tile and its 1-hop halo
           const uint32_t dst1 = smem_u32(T1s + xs * t1_stage_floats) + q * 16;
           const float* src1 = p.t1 + (p.chunk0 + c) * FC + q * 4;
-          for (int i = rg; i < h1; i += 8) {
+          for (int i = (p.tma ? TILE_M : 0) + rg; i < h1; i += 8) {  // (TMA: only the halo rows are left)
             const int v = halo[i];
             if (v >= 0)
               cp_async16(dst1 + i * 128, src1 + (mesh_row0 + v) * p.fin);
@@ -1074,7 +1092,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const DwParams
               sts_f4(dst1 + i * 128, make_float4(0.f, 0.f, 0.f, 0.f));
           }
         }
-        cp_async_arrive_noinc(smem_u32(b_x_full + xs));
+        cp_async_arrive_noinc(xbar);
         if (c == 0 && lt == 0 && it + 1 < my_tiles) fetch_meta(it + 1);
       }
     }
@@ -1901,6 +1919,9 @@ int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, 
   p.t1 = nullptr;
   p.g_unpool = 0;
   p.swap = 0;
+  p.tma = 0;
+  std::memset(&p.tm_x, 0, sizeof(p.tm_x));
+  std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
   return launch_dw_kernels(g, p, fin, fout, false, sm_count, s);
 }
 
@@ -1920,6 +1941,9 @@ int launch_umma_dw_swapped(const DevLevel& g, const float* x, int in_unpool, int
     return P2M_ERR_INVALID;
   }
   DwParams p;
+  p.tma = 0;
+  std::memset(&p.tm_x, 0, sizeof(p.tm_x));
+  std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
   p.x = dz;
   p.in_unpool = 0;
   p.V = g.V;
@@ -1939,6 +1963,10 @@ int launch_umma_dw_swapped(const DevLevel& g, const float* x, int in_unpool, int
   p.t1 = t1_dz;
   p.g_unpool = in_unpool;
   p.swap = 1;
+  if (g.V % TILE_M == 0 && g_umma_tma) {
+    const long long rows = (long long)batch * g.V;
+    p.tma = (make_row_tmap(&p.tm_x, dz, rows, fout, TILE_M) && make_row_tmap(&p.tm_t1, t1_dz, rows, fout, TILE_M)) ? 1 : 0;
+  }
   return launch_dw_kernels(g, p, fout, fin, true, sm_count, s);
 }
 
