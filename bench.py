@@ -507,21 +507,25 @@ def main():
             fl = (2.0 * d["V"] * 3 * d["fin"] * d["fout"] + 2.0 * (2 * nnz0 * d["fin"]) + 2.0 * d["V"] * d["fin"]) * B
             ach = byt / (ms * 1e-3) * 1e-9
             traffic, traffic_src = None, None
-            tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
             if os.path.exists(tpath) and args.precision == "fp16x3":
                 with open(tpath) as fh:
                     tj = json.load(fh)
                 if (tj["V"], tj["fin"], tj["fout"]) == (d["V"], d["fin"], d["fout"]):
                     traffic = tj["layer_dram_bytes"] * B / tj["batch"]   # DRAM bytes scale with the batch
-                    traffic_src = tj["source"] + "; T1 pass + conv kernel of one layer"
+                    traffic_src = tj["source"] + "; T1 pass + conv kernel + plain GEMM of one layer"
             roofline = {"bound": "hbm", "kernel": f"cheb conv V={d['V']} {d['fin']}->{d['fout']} K=3 (layers {dom}): "
-                                                  "k_cheb_t1 + k_cheb_conv_umma<128,3,2>",
+                                                  "k_cheb_t1 + k_cheb_conv_umma<128,3,2> (connected rows) + its plain-GEMM "
+                                                  "mode (representatives of the isolated rows)",
                         "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": traffic,
                         "traffic_source": traffic_src,
                         "ms_per_launch": ms, "algorithmic_bytes": byt, "algorithmic_flops": fl,
                         "tensor_TFLOPs": fl / (ms * 1e-3) * 1e-12, "tensor_frac_of_bf16_peak": fl / (ms * 1e-3) * 1e-12 / bf16_tf,
                         "peak_source": peak_src,
-                        "note": "layer time includes the weight pack/permute launches (<1%); precision " + args.precision}
+                        "note": "achieved = SURVEY 8(d) algorithmic bytes 4*V*(Fin+Fout)*B with the padded V the reference "
+                                "computes / measured layer time (CUDA events inside the library, mean of the layers listed; "
+                                "includes the weight pack launches, <1%); the eval forward computes each class of identical "
+                                "isolated (padding) rows once, see DESIGN.md 4.1; precision " + args.precision}
 
     cpu_baseline = None
     if rank == 0 and args.cpu_sample > 0 and args.mode == "fwd" and args.mesh == "smpl":

@@ -461,6 +461,26 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         bulk_g2s(smem_u32(meta_s + (size_t)m * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
                  smem_u32(b_m_full + m));
       }
+    } else if (tid == (W_XLOAD + 1) * 32 && p.tma) {
+      // ---------------------------------------------------------- own-row TMA issuer (one thread of warp 17)
+      // Issuing the two tensor-map loads of a stage costs the issuing warp ~1.5 k cycles (tools/umma_trace.py, round
+      // 2): done by producer thread 0 that delay sat on every chunk's critical path (all 16 producer warps meet at
+      // the chunk barrier).  This otherwise idle warp only needs the stage to be free (x_empty, arrived by producer
+      // thread 0 after the chunk barrier) — tile and chunk of a stage follow from its index.
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_x)) : "memory");
+      if (t1g) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_t1)) : "memory");
+      const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int n_stage = my_tiles * n_chunk;
+      for (int g2 = 0; g2 < n_stage; ++g2) {
+        const int xs2 = g2 % XS;
+        mbar_wait_relaxed(smem_u32(b_x_empty + xs2), ((g2 / XS) & 1) ^ 1, abort_flag, p.status, 11);
+        const int it2 = g2 / n_chunk, c2 = g2 - it2 * n_chunk;
+        const int own0 = (blockIdx.x + it2 * gridDim.x) * TILE_M;  // V is a multiple of 128: tiles never straddle meshes
+        const uint32_t xbar = smem_u32(b_x_full + xs2);
+        mbar_arrive_expect_tx(xbar, (p.in_unpool ? TILE_M / 2 : TILE_M) * 128 + (t1g ? TILE_M * 128 : 0));
+        tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
+        if (t1g) tma_load_2d(smem_u32(T1s + xs2 * t1_stage_floats), &p.tm_t1, c2 * FC, own0, xbar);
+      }
     }
   } else if (warp == W_BLOAD) {
     // ------------------------------------------------------------ weight-block loader (one thread)
@@ -731,15 +751,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         }
       };
       const uint32_t xbar = smem_u32(b_x_full + xs2);
+      if (tid == 0) trace_ev(p, 0, ptn, 20);
       if (p.tma) {
-        // own rows: one TMA box per operand, issued by one thread and landing asynchronously (the cp.async route
-        // blocks the issuing warps once the load queue is full, i.e. for most of the copy)
-        if (tid == 0) {
-          const int own0 = tile2 * TILE_M;  // V is a multiple of 128 here: tiles never straddle meshes
-          mbar_arrive_expect_tx(xbar, (p.in_unpool ? TILE_M / 2 : TILE_M) * 128 + (t1g ? TILE_M * 128 : 0));
-          tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
-          if (t1g) tma_load_2d(smem_u32(T1s + xs2 * t1_stage_floats), &p.tm_t1, c2 * FC, own0, xbar);
-        }
+        // own rows: one TMA box per operand, issued by warp 17 and landing asynchronously (the cp.async route blocks
+        // the issuing warps once the load queue is full, i.e. for most of the copy); only the halo rows are left
         if (t1g)
           stage_rows(smem_u32(T1s + xs2 * t1_stage_floats) + q * 16, p.t1 + c2 * FC + q * 4, TILE_M, hdr2->h1, false);
       } else {
@@ -749,7 +764,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
                    (p.plain || t1g) ? TILE_M : hdr2->h2, p.in_unpool != 0);
         if (tid == 0) mbar_arrive(xbar);
       }
+      if (tid == 0) trace_ev(p, 0, ptn, 21);
       cp_async_arrive_noinc(xbar);
+      if (tid == 0) trace_ev(p, 0, ptn, 22);
     };
 
     const int xsh = (p.tma && p.in_unpool) ? 1 : 0;  // TMA-staged unpooled input: staged row = tile row >> 1
@@ -811,6 +828,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
         ++ucnt;
         producer_barrier();
+        if (tid == 0 && p.tma) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the TMA issuer may refill it
         if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
         if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1);  // single stage: refill only after everybody is done
         continue;
@@ -898,6 +916,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (tid == 0) trace_ev(p, 0, ptn, 7);
       producer_barrier();  // everybody is done with Xs[xs] and T1s
       if (tid == 0) trace_ev(p, 0, ptn, 8);
+      if (tid == 0 && p.tma) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the TMA issuer may refill it
       if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
       if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1);  // single stage: refill only after everybody is done
     }
@@ -1160,6 +1179,27 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_c
       const int tile = blockIdx.x + it * gridDim.x;
       const int b = tile / p.P, pat = tile - b * p.P;
       const int m = it & 1;
+      // The plain-side tile goes global -> registers -> fp16 blocks.  Its loads are issued FIRST, so that their
+      // latency overlaps the waits below (metadata, and above all g_empty: the previous tile's MMAs still read the
+      // single-buffered plain blocks) instead of following them.
+      float4 pv[2][4];
+      {
+        const int n_rows = min(TILE_M, p.V - pat * TILE_M);
+        const long long r_base = (long long)b * p.V + (long long)pat * TILE_M;
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int i = ps * 64 + rg;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int col = q * 4 + 32 * (jj ^ (rg & 1));
+            pv[ps][jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_rows && col < p.m_cols) {
+              const long long rr = p.g_unpool ? ((r_base + i) >> 1) : (r_base + i);
+              pv[ps][jj] = __ldg(reinterpret_cast<const float4*>(p.g + rr * p.fout_total + p.m_off + col));
+            }
+          }
+        }
+      }
       mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 27);
       {
         const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
@@ -1186,8 +1226,6 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_c
       // plain-side tile (dz, or the layer input in swapped mode) -> (hi, lo) fp16 blocks, MN-major [row][channel]
       mbar_wait(smem_u32(b_g_empty), (it & 1) ^ 1, abort_flag, p.status, 28);
       {
-        const int n_rows = min(TILE_M, p.V - pat * TILE_M);
-        const long long r_base = (long long)b * p.V + (long long)pat * TILE_M;
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           const int i = ps * 64 + rg;
@@ -1196,11 +1234,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_c
             // odd row groups take the 32-channel pieces in the order 1,0,3,2: the two rows of a half-warp then store
             // into different 64-byte bank halves (their swizzle bits agree: consecutive rows)
             const int col = q * 4 + 32 * (jj ^ (rg & 1));  // channel inside this launch's 128-channel slice
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < n_rows && col < p.m_cols) {
-              const long long rr = p.g_unpool ? ((r_base + i) >> 1) : (r_base + i);
-              v = *reinterpret_cast<const float4*>(p.g + rr * p.fout_total + p.m_off + col);
-            }
+            float4 v = pv[ps][jj];
             if (!p.swap) {  // legacy roles: this side is the gradient
               v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
             }

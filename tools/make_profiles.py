@@ -1,0 +1,124 @@
+"""Turn the raw captures a GPU run left in gpurun_out/ into the committed evidence under profiles/ (round 2):
+
+    r2_launches_{fwd,train}.csv + r2_launch_summary_{fwd,train}.txt   ncu --metrics gpu__time_duration.sum launch lists
+    r2_umma_ncu_summary.txt, r2_ncu_traffic.json                      ncu --set full of one V=12288 128->128 layer
+Usage (here, no GPU): python tools/make_profiles.py"""
+import collections
+import csv
+import io
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+
+def launch_summary(tag, cmd):
+    src = os.path.join(GO, f"r2_launches_{tag}.csv")
+    if not os.path.exists(src):
+        return
+    shutil.copy(src, os.path.join(PR, f"r2_launches_{tag}.csv"))
+    rows = list(csv.reader(open(src)))
+    hdr = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    h = rows[hdr]
+    ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    out = [(re.sub(r"\(.*", "", r[ki])[:60], float(r[vi].replace(",", "")) / 1e3) for r in rows[hdr + 1:] if len(r) > vi]
+    n = len(out) // 2
+    tot, cnt = collections.Counter(), collections.Counter()
+    for k, v in out[n:]:
+        tot[k] += v
+        cnt[k] += 1
+    total = sum(tot.values())
+    lines = [cmd, f"second of two steps: {n} launches, {total / 1e3:.2f} ms in total (cold-cache, serialised: compare SHARES, not absolutes)"]
+    for k, v in tot.most_common(30):
+        lines.append(f"  {v / 1e3:9.3f} ms  {100 * v / total:5.1f}%  x{cnt[k]:<3d} {k}")
+    open(os.path.join(PR, f"r2_launch_summary_{tag}.txt"), "w").write("\n".join(lines) + "\n")
+
+
+def ncu_full():
+    rep = os.path.join(GO, "r2_l17.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg"]
+    lines = ["ncu --set full --clock-control none --import-source on -k regex:k_cheb_(conv_umma|t1) -s 77 -c 6: python tools/ncu_forward.py 2",
+             "the two V=12288 128->128 layers of the eval forward at B=256 (bench workload): per layer the T1 pass on the connected-row",
+             "tiles, the conv kernel on those tiles, and the plain GEMM on the representatives of the isolated rows; times under ncu are cold-cache", ""]
+    per = []
+    for n, r in enumerate(rows[2:]):
+        d = dict(zip(hdr, r))
+        per.append(d)
+        lines.append(f"--- kernel {n}")
+        for k in keys:
+            if k in d:
+                lines.append(f"  {k} = {d[k]} {units[hdr.index(k)]}")
+
+    def gb(d, k):
+        v, u = float(d[k].replace(",", "")), units[hdr.index(k)]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+
+    layer = per[:3]
+    traffic = {"source": "profiles/r2_umma_ncu_summary.txt (ncu --set full --clock-control none, first V=12288 128->128 layer of the "
+                         "eval forward at B=256, shipped configuration: padding-vertex elision + duplicate elimination)",
+               "batch": 256, "V": 12288, "fin": 128, "fout": 128, "kernels": {}, "layer_dram_bytes": 0.0}
+    for d, name in zip(layer, ("k_cheb_t1 (connected rows)", "k_cheb_conv_umma<128,3,2> (connected rows)",
+                               "k_cheb_conv_umma<128,3,2> plain (isolated representatives)")):
+        rd, wr = gb(d, "dram__bytes_read.sum"), gb(d, "dram__bytes_write.sum")
+        traffic["kernels"][name] = {"dram_read_bytes": rd, "dram_write_bytes": wr,
+                                    "ms_under_ncu": float(d["gpu__time_duration.sum"])}
+        traffic["layer_dram_bytes"] += rd + wr
+    json.dump(traffic, open(os.path.join(PR, "r2_ncu_traffic.json"), "w"), indent=1)
+    # shared-memory wavefronts of the conv kernel by opcode (source page)
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:conv_umma"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(src)))
+    his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    if his:
+        hi, end = his[0], (his[1] if len(his) > 1 else len(rows))
+        h = rows[hi]
+        idx = {c: i for i, c in enumerate(h)}
+        seen, u = set(), []
+        for r in rows[hi + 1:end]:
+            if len(r) == len(h) and r[0].startswith("0x") and r[0] not in seen:
+                seen.add(r[0])
+                u.append(r)
+        by, ex, cnt = collections.Counter(), collections.Counter(), collections.Counter()
+        stalls = collections.Counter()
+        for r in u:
+            m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[idx["Source"]].strip())
+            op = m.group(2) if m else "?"
+            w = int(r[idx["L1 Wavefronts Shared"]] or 0)
+            if w:
+                by[op] += w
+                ex[op] += int(r[idx["L1 Wavefronts Shared Excessive"]] or 0)
+                cnt[op] += int(r[idx["Instructions Executed"]] or 0)
+            for c in h:
+                if c.startswith("stall_") and "Not Issued" not in c and r[idx[c]]:
+                    stalls[c] += int(r[idx[c]])
+        chunks = 13824 * 4
+        lines += ["", "conv kernel on the connected-row tiles (13824 tiles x 4 feature chunks): shared-memory wavefronts per chunk by opcode",
+                  f"  total {sum(by.values()) / chunks:.0f} LSU wavefronts per chunk (+ 1152 of tcgen05 operand reads, SS mode, fp16x3)"]
+        for op, w in by.most_common(10):
+            lines.append(f"  {op:26s} {w / chunks:8.1f} wavefronts  {ex[op] / chunks:7.1f} excessive  {cnt[op] / chunks:7.1f} instructions")
+        s = sum(stalls.values())
+        lines.append("  stall mix: " + ", ".join(f"{k[6:]} {100 * v / s:.1f}%" for k, v in stalls.most_common(8)))
+    open(os.path.join(PR, "r2_umma_ncu_summary.txt"), "w").write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    launch_summary("fwd", "ncu --metrics gpu__time_duration.sum --clock-control none --csv: python tools/ncu_forward.py 2   (eval forward, B=256, SMPL-size hierarchy, fp16x3)")
+    launch_summary("train", "ncu --metrics gpu__time_duration.sum --clock-control none --csv: python tools/ncu_forward.py 2 256 train   (fwd+bwd, L1 loss)")
+    ncu_full()
+    print("profiles updated")
