@@ -334,6 +334,12 @@ struct KParams {
                          //    the consecutive rows [128 pat, 128 pat + 128)
   const float* head_wt;  // optional fused thin head (N == 64): epilogue writes head_z[row][12] = y_row * head_wt[64][12]
   float* head_z;
+  // Dense GEMM mode (launch_umma_gemm: PoseNet's Linear layers): the A operand is PRE-PACKED like a weight image
+  // (k_pack_plain on the activation matrix: one 16 KB block per (128-row tile, 32-feature chunk)), so both operands of
+  // every K-block arrive by cp.async.bulk and no producer warp runs; blockIdx.y selects an N-wide slice of the output
+  // columns (its weight image, epilogue vectors and output / residual columns).
+  const unsigned char* apack;
+  long long wslice_bytes;  // bytes of one N-slice's weight image
   int tma;           // 1: the tile's own rows of x (and t1) arrive by one 2-D TMA load each (T1-given / plain mode on
                      //    levels whose size is a multiple of 128); with in_unpool the x box is the 64 source rows
   CUtensorMap tm_x, tm_t1;
@@ -412,7 +418,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(b_ab_full + s), W_PROD + 1);  // one elected arrive per producer warp + the weight loader
+      // one elected arrive per producer warp + the weight loader (dense GEMM mode: the loader alone)
+      mbar_init(smem_u32(b_ab_full + s), p.apack != nullptr ? 1 : W_PROD + 1);
       mbar_init(smem_u32(b_ab_empty + s), 1);
     }
     for (int s = 0; s < XS; ++s) {
@@ -431,12 +438,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     fence_barrier_init();
   }
   const float a_scale = p.a_scale ? *p.a_scale : 1.f;
+  const int ecol0 = (int)blockIdx.y * N;  // first output column of this CTA's slice (0 outside the dense GEMM mode)
   for (int n = threadIdx.x; n < N; n += NUM_THREADS2) {
-    const float sc = (p.ep.scale ? p.ep.scale[n] : 1.f) / a_scale;
-    const float sh = p.ep.scale ? p.ep.shift[n] : 0.f;
-    const float bi = p.ep.bias ? p.ep.bias[n] : 0.f;
+    const float sc = (p.ep.scale ? p.ep.scale[ecol0 + n] : 1.f) / a_scale;
+    const float sh = p.ep.scale ? p.ep.shift[ecol0 + n] : 0.f;
+    const float bi = p.ep.bias ? p.ep.bias[ecol0 + n] : 0.f;
     ep_mul[n] = W_INV_SCALE * sc;
-    ep_add[n] = fmaf(bi, p.ep.scale ? p.ep.scale[n] : 1.f, sh);
+    ep_add[n] = fmaf(bi, p.ep.scale ? p.ep.scale[ecol0 + n] : 1.f, sh);
   }
   if (N == 64 && p.head_z != nullptr)
     for (int i = threadIdx.x; i < 64 * 12; i += NUM_THREADS2) head_w_s[i] = p.head_wt[i];
@@ -450,7 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     // ------------------------------------------------------------ tile-metadata loader (one thread, cp.async.bulk)
     // (the X / T1 rows themselves are staged by the producers: two dedicated loader warps could not keep up once the
     //  first sparse product moved out of this kernel — 16 spinning producer warps starve them of issue slots)
-    if (tid == W_XLOAD * 32) {
+    if (tid == W_XLOAD * 32 && p.apack == nullptr) {
       const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       for (int it = 0; it < my_tiles; ++it) {
         const int pat = (blockIdx.x + it * gridDim.x) % p.P;
@@ -494,8 +502,15 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           const uint32_t par = (ucnt / NS) & 1;
           mbar_wait_relaxed(smem_u32(b_ab_empty + s), par ^ 1, abort_flag, p.status, 4);
           trace_ev(p, 1, tn, 10 + u);
-          mbar_arrive_expect_tx(smem_u32(b_ab_full + s), B_BLOCK_BYTES);
-          bulk_g2s(smem_u32(ring + s * SLOT_BYTES + A_BLOCK_BYTES), p.wpack + (size_t)u * B_BLOCK_BYTES, B_BLOCK_BYTES,
+          const unsigned char* wsl = p.wpack + (size_t)blockIdx.y * (size_t)p.wslice_bytes;
+          if (p.apack != nullptr) {  // dense GEMM mode: the tile's pre-packed A block of chunk u rides along
+            mbar_arrive_expect_tx(smem_u32(b_ab_full + s), B_BLOCK_BYTES + A_BLOCK_BYTES);
+            bulk_g2s(smem_u32(ring + s * SLOT_BYTES), p.apack + ((size_t)tile * uses + u) * A_BLOCK_BYTES, A_BLOCK_BYTES,
+                     smem_u32(b_ab_full + s));
+          } else {
+            mbar_arrive_expect_tx(smem_u32(b_ab_full + s), B_BLOCK_BYTES);
+          }
+          bulk_g2s(smem_u32(ring + s * SLOT_BYTES + A_BLOCK_BYTES), wsl + (size_t)u * B_BLOCK_BYTES, B_BLOCK_BYTES,
                    smem_u32(b_ab_full + s));
         }
       }
@@ -568,13 +583,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (p.ep.res != nullptr) {
         // pull this tile's residual rows into L2 while its main loop is still running: the reads below then pay
         // an L2 hit instead of a DRAM round trip per batch
-        const int lpr = (p.ep.res_F * 4 + 127) >> 7;  // 128-byte lines per residual row
+        // 128-byte lines per residual row (dense GEMM mode: only this CTA's N-column slice of the row)
+        const int lpr = ((p.apack != nullptr ? N : p.ep.res_F) * 4 + 127) >> 7;
         for (int j = lane; j < 32 * lpr; j += 32) {
           const int rr = j / lpr, ln = j - rr * lpr;
           const int vtx = own_w[rr];
           if (vtx >= 0) {
             const long long r = mesh0 + vtx;
-            prefetch_l2(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + ln * 32);
+            prefetch_l2(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + (p.apack != nullptr ? ecol0 : 0) + ln * 32);
           }
         }
       }
@@ -656,7 +672,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
                 const int vtx = own_w[rr];
                 const long long r = mesh0 + vtx;
                 rv[i] = (vtx >= 0)
-                            ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + n))
+                            ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + ecol0 + n))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
@@ -690,7 +706,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
                     }
                   }
                 }
-                *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + n) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + ecol0 + n) = make_float4(o[0], o[1], o[2], o[3]);
               }
             }
           }
@@ -702,7 +718,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 2);
       if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
     }
-  } else {
+  } else if (p.apack == nullptr) {
     // ------------------------------------------------------------ producers (16 warps)
     const int q = tid & 7;     // float4 lane inside the 32-feature chunk
     const int rg = tid >> 3;   // row group 0..63
@@ -1521,6 +1537,8 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   }
   p.n_tiles = a.batch * p.P;
   p.wpack = static_cast<const unsigned char*>(a.wpack);
+  p.apack = nullptr;
+  p.wslice_bytes = 0;
   p.zero_row = zero_row;
   p.ep = to_dev(a.ep);
   p.res_identity = (a.ep.res != nullptr && a.ep.res_F == a.fout) ? 1 : 0;
@@ -2048,7 +2066,7 @@ bool umma_conv_supported(const DevLevel& g, int fin, int fout) {
 }
 
 __global__ void __launch_bounds__(256) k_pack_plain(const float* __restrict__ Bmat, long long ld_n, long long ld_k, int N,
-                                                    int K, unsigned char* __restrict__ out) {
+                                                    int K, unsigned char* __restrict__ out, float W_SCALE = 64.f) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
   const int total = (K / FC) * N * 8;
   if (idx >= total) return;
@@ -2151,6 +2169,113 @@ int launch_umma_pack_iso_t(const float* W, float c, int fin, int fout, void* wpa
 }
 
 size_t umma_plain_pack_bytes(int N, int K) { return (size_t)(K / FC) * N * 128; }
+
+// ---------------------------------------------------------------- dense GEMM on the conv kernel's plain mode
+// A operand image of a row-major activation matrix X [M, K] (K % 32 == 0): per (128-row tile, 32-column chunk) one
+// 16 KB block [128 rows][hi 32 | lo 32] fp16, 128B-swizzled, rows >= M zero — what the producers would have built.
+__global__ void __launch_bounds__(256) k_pack_rows(const float* __restrict__ X, int M, int K, unsigned char* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int n_chunk = K / FC;
+  const long long total = (long long)((M + TILE_M - 1) / TILE_M) * n_chunk * TILE_M * 8;
+  if (idx >= total) return;
+  const int j = (int)(idx & 7);
+  const int row = (int)((idx >> 3) % TILE_M);
+  const long long blk = (idx >> 3) / TILE_M;  // tile * n_chunk + c
+  const int c = (int)(blk % n_chunk);
+  const long long r = (blk / n_chunk) * TILE_M + row;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v = (r < M) ? X[r * K + c * FC + (j & 3) * 8 + e] : 0.f;
+    const __half hi = __float2half_rn(v);
+    h[e] = (j < 4) ? hi : __float2half_rn(v - __half2float(hi));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)blk * A_BLOCK_BYTES + sw128_off(row, j)) = *reinterpret_cast<const uint4*>(h);
+}
+// Weight images of ALL output-column slices in one launch: slice j (rows [j ns, (j+1) ns) of W [n_real, K], rows >=
+// n_real zero) -> K/32 blocks of ns rows x 128 bytes [Whi | Wlo] (scaled by 2^6 like every weight image).
+__global__ void __launch_bounds__(256) k_pack_w_sliced(const float* __restrict__ W, int n_real, int N, int K, int ns,
+                                                       unsigned char* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int n_chunk = K / FC;
+  const long long total = (long long)N * n_chunk * 8;
+  if (idx >= total) return;
+  const int j = (int)(idx & 7);
+  const int nl = (int)((idx >> 3) % ns);
+  const long long blk = (idx >> 3) / ns;  // slice * n_chunk + c
+  const int c = (int)(blk % n_chunk);
+  const int n = (int)(blk / n_chunk) * ns + nl;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float w = (n < n_real) ? W[(size_t)n * K + c * FC + (j & 3) * 8 + e] * W_SCALE : 0.f;
+    const __half hi = __float2half_rn(w);
+    h[e] = (j < 4) ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  *reinterpret_cast<uint4*>(out + (size_t)blk * ns * 128 + sw128_off(nl, j)) = *reinterpret_cast<const uint4*>(h);
+}
+size_t umma_gemm_apack_bytes(int M, int K) { return (size_t)((M + TILE_M - 1) / TILE_M) * (K / FC) * A_BLOCK_BYTES; }
+size_t umma_gemm_wpack_bytes(int N, int K) { return (size_t)(K / FC) * N * 128; }
+bool umma_gemm_supported(int M, int N, int K) { return M > 0 && K >= FC && K % FC == 0 && N >= 64 && N % 64 == 0; }
+
+namespace {
+template <int N>
+int launch_gemm_cfg(KParams p, int n_slices, int sm_count, cudaStream_t s) {
+  constexpr int NS = (N == 256) ? 2 : 3;
+  const size_t smem = smem_bytes_dims(N, NS, 1, 0, 0, 0, 2);
+  auto kern = k_cheb_conv_umma<N, NS, 1, 0>;
+  P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.wslice_bytes = (long long)umma_gemm_wpack_bytes(N, p.fin);
+  const dim3 grid(std::min(p.n_tiles, sm_count), n_slices);
+  kern<<<grid, NUM_THREADS2, smem, s>>>(p);
+  P2M_LAUNCH_OK();
+  return P2M_OK;
+}
+}  // namespace
+
+// Y [M, N] = epilogue( X [M, K] * W [N, K]^T )  on tcgen05 (fp16x3): X and W are packed into operand images first
+// (apack / wpack: caller-provided scratch of umma_gemm_{a,w}pack_bytes), then every K-block of both operands is
+// streamed by cp.async.bulk into the conv kernel's A/B ring — no producer warps, one CTA per (128-row tile, output
+// column slice).  The epilogue vectors and an identity residual (ep.res with res_F == N) are indexed by output column.
+int launch_umma_gemm(const float* X, const float* W, int M, int N, int K, const Epilogue& ep, float* Y, void* apack,
+                     void* wpack, int* status, int sm_count, cudaStream_t s, int n_real) {
+  if (n_real <= 0 || n_real > N) n_real = N;  // W has n_real rows; output columns >= n_real are zero-weight padding
+  if (!umma_gemm_supported(M, N, K) || (ep.res != nullptr && ep.res_F != N)) {
+    set_error("umma_gemm: unsupported shape");
+    return P2M_ERR_INVALID;
+  }
+  {
+    const long long total = (long long)((M + TILE_M - 1) / TILE_M) * (K / FC) * TILE_M * 8;
+    k_pack_rows<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(X, M, K, static_cast<unsigned char*>(apack));
+    P2M_LAUNCH_OK();
+  }
+  const int tiles = (M + TILE_M - 1) / TILE_M;
+  const int ns = (tiles * (N / 128) < sm_count || N % 128 != 0) ? 64 : ((tiles * (N / 256) < sm_count || N % 256 != 0) ? 128 : 256);
+  {
+    const long long total = (long long)N * (K / FC) * 8;
+    k_pack_w_sliced<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, n_real, N, K, ns, static_cast<unsigned char*>(wpack));
+    P2M_LAUNCH_OK();
+  }
+  KParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.V = M;                // one "mesh" of M rows: the epilogue masks rows >= V of the last tile
+  p.P = tiles;
+  p.fin = K;
+  p.n_tiles = tiles;
+  p.wpack = static_cast<const unsigned char*>(wpack);
+  p.apack = static_cast<const unsigned char*>(apack);
+  p.ep = to_dev(ep);
+  p.res_identity = (ep.res != nullptr) ? 1 : 0;
+  p.plain = 1;
+  p.ldy = N;
+  p.y = Y;
+  p.status = status;
+  switch (ns) {
+    case 64: return launch_gemm_cfg<64>(p, N / ns, sm_count, s);
+    case 128: return launch_gemm_cfg<128>(p, N / ns, sm_count, s);
+    default: return launch_gemm_cfg<256>(p, N / ns, sm_count, s);
+  }
+}
 
 int launch_umma_pack_plain(const float* Bmat, long long ld_n, long long ld_k, int N, int K, void* wpack, cudaStream_t s) {
   const int total = (K / FC) * N * 8;

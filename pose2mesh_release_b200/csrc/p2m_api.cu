@@ -1331,6 +1331,14 @@ __global__ void __launch_bounds__(256) k_bn_relu_rows(const float* __restrict__ 
   const float sc = gamma[f] / sqrtf(rv[f] + 1e-5f);
   y[i] = fmaxf(fmaf(x[i] - rm[f], sc, beta[f]), 0.f);
 }
+__global__ void __launch_bounds__(256) k_take_cols(const float* __restrict__ src, int ld, const float* __restrict__ bias,
+                                                   int n_col, long long n, float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = i / n_col;
+  const int c = (int)(i - r * n_col);
+  dst[i] = src[r * ld + c] + bias[c];
+}
 __global__ void __launch_bounds__(256) k_pose_combine(const float* __restrict__ pose2d, const float* __restrict__ pose3d,
                                                       long long n_joint_rows, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
@@ -1347,7 +1355,10 @@ extern "C" {
 
 size_t p2m_posenet_workspace_bytes(int batch, int hidden) {
   if (batch <= 0 || hidden <= 0) return 0;
-  return 3 * align_up((size_t)batch * hidden * 4) + align_up(2 * (size_t)hidden * 4);
+  size_t n = 3 * align_up((size_t)batch * hidden * 4) + align_up(2 * (size_t)hidden * 4) + ALIGN;
+  if (umma_gemm_supported(batch, hidden, hidden))  // operand images of the hidden x hidden GEMMs (tcgen05 path)
+    n += align_up(umma_gemm_apack_bytes(batch, hidden)) + align_up(umma_gemm_wpack_bytes(hidden, hidden));
+  return n;
 }
 
 int p2m_posenet_forward(const p2m_posenet_params_t* P, const float* pose2d, float* pose3d, float* pose_combine, int B,
@@ -1368,6 +1379,23 @@ int p2m_posenet_forward(const p2m_posenet_params_t* P, const float* pose2d, floa
   float* a = b.take<float>((size_t)B * H);
   float* h = b.take<float>((size_t)B * H);
   float* sc = b.take<float>(2 * (size_t)H);
+  int* status = b.take<int>(1);
+  // The two H x H GEMMs of every stage run on tcgen05 (fp16x3, both operands streamed by cp.async.bulk:
+  // launch_umma_gemm) when H allows; the thin first / last layers (K = 2J, N = 3J) stay on the fp32 SIMT GEMM.
+  const bool tc = umma_gemm_supported(B, H, H);
+  void* apack = tc ? b.take<unsigned char>(umma_gemm_apack_bytes(B, H)) : nullptr;
+  void* wpack = tc ? b.take<unsigned char>(umma_gemm_wpack_bytes(H, H)) : nullptr;
+  int sm_count = 148;
+  if (tc) {
+    int dev = 0;
+    P2M_CUDA_OK(cudaGetDevice(&dev));
+    P2M_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    P2M_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), s));
+  }
+  auto big_gemm = [&](const float* X, const float* Wm, const Epilogue& e, float* Y) -> int {
+    if (tc) return launch_umma_gemm(X, Wm, B, H, H, e, Y, apack, wpack, status, sm_count, s);
+    return launch_gemm(X, H, Wm, H, 0, Y, H, B, H, H, e, s);
+  };
   Epilogue e1;
   e1.bias = P->w1_b;
   P2M_TRY(launch_gemm(pose2d, 2 * J, P->w1_w, 2 * J, 0, y, H, B, H, 2 * J, e1, s));
@@ -1388,18 +1416,27 @@ int p2m_posenet_forward(const p2m_posenet_params_t* P, const float* pose2d, floa
     ea.scale = sc;
     ea.shift = sc + H;
     ea.relu = 1;
-    P2M_TRY(launch_gemm(a, H, S.w1_w, H, 0, h, H, B, H, H, ea, s));
+    P2M_TRY(big_gemm(a, S.w1_w, ea, h));
     // y' = y + h Wb^T + bb  (written to `a`, then the buffers swap roles)
     Epilogue eb;
     eb.bias = S.w2_b;
     eb.res = y;
     eb.res_F = H;
-    P2M_TRY(launch_gemm(h, H, S.w2_w, H, 0, a, H, B, H, H, eb, s));
+    P2M_TRY(big_gemm(h, S.w2_w, eb, a));
     std::swap(y, a);
   }
-  Epilogue e2;
-  e2.bias = P->w2_b;
-  P2M_TRY(launch_gemm(y, H, P->w2_w, H, 0, pose3d, 3 * J, B, 3 * J, H, e2, s));
+  if (tc && 3 * J <= 64) {
+    // the K = H reduction of the output layer on tcgen05 as well: N padded to 64 zero-weight columns (two CTAs of
+    // the fp32 SIMT GEMM would walk the 4096-long reduction alone), then the 3J real columns are copied out + bias
+    P2M_TRY(launch_umma_gemm(y, P->w2_w, B, 64, H, Epilogue(), h, apack, wpack, status, sm_count, s, 3 * J));
+    const long long n = (long long)B * 3 * J;
+    k_take_cols<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h, 64, P->w2_b, 3 * J, n, pose3d);
+    P2M_LAUNCH_OK();
+  } else {
+    Epilogue e2;
+    e2.bias = P->w2_b;
+    P2M_TRY(launch_gemm(y, H, P->w2_w, H, 0, pose3d, 3 * J, B, 3 * J, H, e2, s));
+  }
   if (pose_combine != nullptr) {
     const long long n = (long long)B * J;
     k_pose_combine<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pose2d, pose3d, n, pose_combine);

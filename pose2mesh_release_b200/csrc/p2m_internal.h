@@ -279,6 +279,14 @@ int launch_umma_pack_iso(const float* W, float c, int fin, int fout, void* wpack
 int launch_umma_pack_weights_t(const float* W /*[fout, fin*3]*/, int fin, int fout, void* wpack, cudaStream_t s);
 int launch_umma_pack_iso_t(const float* W, float c, int fin, int fout, void* wpack, cudaStream_t s);
 int launch_umma_conv(const UmmaConvArgs& a, int* status_flag, const float* zero_row, int sm_count, cudaStream_t s);
+// Dense GEMM on tcgen05 (fp16x3): Y [M, N] = epilogue(X [M, K] W [N, K]^T), K % 32 == 0, N % 64 == 0; apack / wpack are
+// scratch of umma_gemm_apack_bytes(M, K) / umma_gemm_wpack_bytes(N, K); ep vectors and an identity residual
+// (ep.res, res_F == N) are indexed by output column.
+bool umma_gemm_supported(int M, int N, int K);
+size_t umma_gemm_apack_bytes(int M, int K);
+size_t umma_gemm_wpack_bytes(int N, int K);
+int launch_umma_gemm(const float* X, const float* W, int M, int N, int K, const Epilogue& ep, float* Y, void* apack,
+                     void* wpack, int* status, int sm_count, cudaStream_t s, int n_real = 0 /* rows of W if < N */);
 // out[ro, :] = sum over the logical rows r of physical row ro (r = ro, or 2 ro and 2 ro + 1 under the virtual unpool)
 // of  dxl[r, :] + resample^T(g_res[r, :])   (g_res may be null)
 int launch_dx_finish(const float* dxl, int rows, int F, const float* g_res, int res_Fout, const InterpTable* it,

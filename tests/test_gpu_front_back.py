@@ -9,6 +9,10 @@ from helpers import graph_from_fixture, load_npz, rel_err
 
 pytestmark = pytest.mark.gpu
 
+# PoseNet's 4096-long reductions on tcgen05 (fp16 hi/lo split = 22 mantissa bits per operand, fp32 accumulate) land at
+# ~2e-5 of max|pose3d|; the bound is the path's 1e-4 (north_star), with a factor 2 of margin
+TOL_POSE = 5e-5
+
 
 def dev():
     return torch.device("cuda:0")
@@ -35,16 +39,17 @@ def test_posenet_eval_matches_reference_golden_and_oracle():
     pose2d = torch.from_numpy(z["pose2d"])
     with torch.no_grad():
         pose3d, comb = net.forward_native(pose2d.to(dev()), with_combine=True)
-        assert rel_err(net(pose2d.to(dev()).reshape(8, -1)), torch.from_numpy(z["pose3d"])) < 1e-5   # nn.Module path
+        assert rel_err(net(pose2d.to(dev()).reshape(8, -1)), torch.from_numpy(z["pose3d"])) < TOL_POSE   # nn.Module path
     assert pose3d.shape == (8, 51) and comb.shape == (8, 17, 5)
-    assert rel_err(pose3d, torch.from_numpy(z["pose3d"])) < 1e-5            # the unmodified reference's PoseNet
-    np.testing.assert_allclose(comb.cpu().numpy(), z["pose_combine"], rtol=1e-5, atol=1e-7)
+    assert rel_err(pose3d, torch.from_numpy(z["pose3d"])) < TOL_POSE        # the unmodified reference's PoseNet
+    np.testing.assert_allclose(comb.cpu().numpy()[..., :2], z["pose_combine"][..., :2], rtol=0, atol=0)
+    np.testing.assert_allclose(comb.cpu().numpy()[..., 2:], z["pose_combine"][..., 2:], rtol=0, atol=TOL_POSE * 1e-3)
     g = torch.Generator().manual_seed(9)
     x = torch.randn(300, 34, generator=g)                                    # a ragged batch (GEMM tile tails)
     with torch.no_grad():
         got = net.forward_native(x.to(dev()))
         ref = do.posenet_forward(sd, x)
-    assert rel_err(got, ref) < 1e-5
+    assert rel_err(got, ref) < TOL_POSE
 
 
 def test_flat_pose2mesh_matches_oracle_pipeline():
@@ -68,7 +73,7 @@ def test_flat_pose2mesh_matches_oracle_pipeline():
     with torch.no_grad():
         p3 = do.posenet_forward(sd_p, pose2d.reshape(5, -1))
         yo = mo.forward(sd_m, mo.laplacians_to_torch(mats), do.flat_pose2mesh_input(pose2d, p3), training=False)
-    assert pose3d.shape == (5, 17, 3) and rel_err(pose3d.reshape(5, -1), p3) < 1e-5
+    assert pose3d.shape == (5, 17, 3) and rel_err(pose3d.reshape(5, -1), p3) < TOL_POSE
     assert rel_err(mesh, yo) < 1e-4
     # the callers' tail (base.py:130-131): gather + joint regression
     perm_rev = np.asarray(zg["perm_reverse"])
