@@ -207,6 +207,8 @@ struct WsMap {
   // training: saved tensors
   std::vector<float*> z, a, mean, invstd, scale, shift, wp;
   float* fc_out = nullptr;
+  unsigned char* fc_apack = nullptr;  // operand images of the fc GEMM on tcgen05 (launch_umma_gemm)
+  unsigned char* fc_wpack = nullptr;
   size_t bytes = 0;
 };
 
@@ -219,6 +221,10 @@ WsMap map_workspace(const p2m_model* m, int B, int training, void* base) {
   w.wpack = b.take<unsigned char>(std::max(s.max_wpack, (size_t)16));
   w.scale_scratch = b.take<float>(2 * (size_t)s.max_f);
   w.sums = b.take<double>(2 * (size_t)s.max_f);
+  if (umma_gemm_supported(B, m->fc_out, m->fc_in)) {
+    w.fc_apack = b.take<unsigned char>(umma_gemm_apack_bytes(B, m->fc_in));
+    w.fc_wpack = b.take<unsigned char>(umma_gemm_wpack_bytes(m->fc_out, m->fc_in));
+  }
   const size_t nl = m->layers.size();
   if (!training) {
     for (int i = 0; i < 3; ++i) w.rot[i] = b.take<float>(s.max_act);
@@ -862,7 +868,11 @@ static int meshnet_forward_impl(p2m_model_t* m, const p2m_params_t* P, const flo
       } else {
         out = w.fc_out;
       }
-      P2M_TRY(launch_gemm(cur, m->fc_in, P->fc_w, m->fc_in, 0, out, m->fc_out, B, m->fc_out, m->fc_in, ep, s));
+      if (m->precision == P2M_PREC_FP16X3_TC && w.fc_apack != nullptr)  // dense GEMM on tcgen05 (fp16x3)
+        P2M_TRY(launch_umma_gemm(cur, P->fc_w, B, m->fc_out, m->fc_in, ep, out, w.fc_apack, w.fc_wpack, m->kernel_status,
+                                 m->sm_count, s));
+      else
+        P2M_TRY(launch_gemm(cur, m->fc_in, P->fc_w, m->fc_in, 0, out, m->fc_out, B, m->fc_out, m->fc_in, ep, s));
       cur = out;
       cur_unpool = 0;
     } else if (blk.out_unpool) {

@@ -11,7 +11,8 @@ Outputs (all small, committed):
                          (full CSR for the small cases, digests for the 6890-vertex case)
     meshnet_<case>.npz   Pose2Mesh forward (eval + train) and backward of the reference for seeded
                          weights/inputs: outputs, BN running stats, input gradient, per-parameter
-                         gradient digests, per-parameter init digests (torch.manual_seed(123))
+                         gradient digests, per-parameter init digests (torch.manual_seed(123)); and the
+                         train step once more with the ReLUs held open (strict/*: BatchNorm bias +6)
     cheb_conv.npz        one graph_conv_cheby() call of the reference (with and without BatchNorm)
     demo_input.npz       the reference's only hot-path input fixture demo/h36m_joint_input.npy
 """
@@ -141,8 +142,27 @@ def save_meshnet(gu, mn, name, batch=2):
     for k, v in model.state_dict().items():
         if "running" in k:
             out["after/" + k] = v.numpy().copy()
+    # ---- the same with the ReLUs held open (every BatchNorm bias = +6): no activation sits near its kink, so two
+    #      correct fp32 implementations agree on every gradient to rounding — the fixture for TIGHT gradient digests
+    sd_open = {k: v.clone() for k, v in sd0.items()}
+    for k in sd_open:
+        if k.startswith("bn.") and k.endswith(".bias"):
+            sd_open[k].fill_(6.0)
+    model.load_state_dict(sd_open)
+    model.train()
+    model.zero_grad()
+    xs = x.clone().requires_grad_(True)
+    with ref_shim.cpu_cuda_noop():
+        ys = model(xs)
+        ls = (ys - tgt).abs().mean()
+        ls.backward()
+    out["strict/y_train"] = ys.detach().numpy()
+    out["strict/loss"] = np.array(ls.item())
+    out["strict/dx"] = xs.grad.numpy()
+    for k, p in model.named_parameters():
+        out["strict/grad/" + k] = tensor_digest(p.grad)
     np.savez_compressed(os.path.join(HERE, f"meshnet_{name}.npz"), **out)
-    print("wrote meshnet", name, tuple(y_eval.shape), "loss", loss.item())
+    print("wrote meshnet", name, tuple(y_eval.shape), "loss", loss.item(), "strict loss", ls.item())
 
 
 def save_cheb_conv(gu, cgc):

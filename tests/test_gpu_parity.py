@@ -101,16 +101,47 @@ def test_meshnet_train_step_matches_reference_golden(name, precision):
     assert ok, ("dx", info)
     for k, p in model.named_parameters():
         got, ref = tensor_digest(p.grad), z["grad/" + k]
-        # digests of the reference's gradients per tensor: sum |g| within 2e-3 and sum g^2 within 4e-3 (the squared
-        # norm moves by twice the relative error; the ReLUs are live here, see grad_close).  Conv biases in front of
-        # a BatchNorm have a mathematically zero gradient: absolute floor.
-        assert abs(got[1] - ref[1]) <= 2e-3 * ref[1] + 1e-6, (k, got[1], ref[1])
-        assert abs(got[2] - ref[2]) <= 4e-3 * ref[2] + 1e-12, (k, got[2], ref[2])
+        # digests of the reference's gradients per tensor with LIVE ReLUs: a unit within fp32 rounding of its kink
+        # flips between two correct implementations (see grad_close), so this is the loose check; the tight one
+        # (2e-3) runs on the open-ReLU fixture below.  Conv biases in front of a BatchNorm have a mathematically zero
+        # gradient: absolute floor.
+        assert abs(got[1] - ref[1]) <= 1e-2 * ref[1] + 1e-6, (k, got[1], ref[1])
+        assert abs(got[2] - ref[2]) <= 2e-2 * ref[2] + 1e-12, (k, got[2], ref[2])
     for k, v in model.state_dict().items():
         if "running" in k:
             np.testing.assert_allclose(v.cpu().numpy(), z["after/" + k], rtol=1e-4, atol=1e-6, err_msg=k)
         if "num_batches_tracked" in k:
             assert int(v) == 1
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", ["smpl_small", "mano_like"])
+def test_meshnet_train_step_matches_reference_golden_strict(name, precision):
+    """The reference's own train step with the ReLUs held open (strict/* of the fixture: every BatchNorm bias = +6, no
+    activation near its kink): outputs, loss, dx element-wise at 1e-3 of max, and the per-tensor gradient digests
+    sum |g| and sum g^2 within 2e-3."""
+    z = load_npz(f"meshnet_{name}.npz")
+    model, mats, mano = make_model(name, precision)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k in sd:
+        if k.startswith("bn.") and k.endswith(".bias"):
+            sd[k].fill_(6.0)
+    model.load_state_dict(sd)
+    model.train()
+    x = torch.from_numpy(z["x"]).to(dev()).requires_grad_(True)
+    y = model(x)
+    assert per_mesh_rel_err(y, torch.from_numpy(z["strict/y_train"])) < TOL_Y
+    loss = (y - torch.from_numpy(z["target"]).to(dev())).abs().mean()
+    assert abs(loss.item() - float(z["strict/loss"])) < 1e-5 * float(z["strict/loss"]) + 1e-6
+    loss.backward()
+    ok, info = grad_close(x.grad, torch.from_numpy(z["strict/dx"]), strict=True)
+    assert ok, ("dx", info)
+    floor1 = 1e-3 * max(float(z["strict/grad/" + k][1]) / p.numel() for k, p in model.named_parameters())
+    for k, p in model.named_parameters():
+        got, ref = tensor_digest(p.grad), z["strict/grad/" + k]
+        # (conv biases in front of a BatchNorm: mathematically zero, the reference holds rounding noise -> floors)
+        assert abs(got[1] - ref[1]) <= 2e-3 * ref[1] + floor1 * p.numel(), (k, got[1], ref[1])
+        assert abs(got[2] - ref[2]) <= 2e-3 * ref[2] + (floor1 ** 2) * p.numel(), (k, got[2], ref[2])
 
 
 def _gradient_parity(precision, open_relus):

@@ -117,6 +117,26 @@ def test_meshnet_oracle_matches_reference(name):
         if "running" in k:
             np.testing.assert_allclose(v.numpy(), z["after/" + k], rtol=1e-4, atol=1e-6, err_msg=k)
 
+    # the open-ReLU train step of the reference (strict/*: every BatchNorm bias = +6): the fixture of the tight GPU digests
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd0.items()}
+    with torch.no_grad():
+        for k in sd:
+            if k.startswith("bn.") and k.endswith(".bias"):
+                sd[k].fill_(6.0)
+    xs = x.clone().requires_grad_(True)
+    ys = mo.forward(sd, laps, xs, mano=mano, training=True)
+    assert rel_err(ys, torch.from_numpy(z["strict/y_train"])) < 1e-5
+    ls = (ys - torch.from_numpy(z["target"])).abs().mean()
+    assert abs(ls.item() - float(z["strict/loss"])) < 1e-5
+    ls.backward()
+    assert rel_err(xs.grad, torch.from_numpy(z["strict/dx"])) < 1e-4
+    for k, v in sd.items():
+        if v.requires_grad:
+            got, ref = tensor_digest(v.grad), z["strict/grad/" + k]
+            assert abs(got[1] - ref[1]) <= 1e-3 * ref[1] + 1e-5, k
+            assert abs(got[2] - ref[2]) <= 2e-3 * ref[2] + 1e-10, k
+
 
 @pytest.mark.parametrize("name", ["smpl_small", "smpl_like"])
 def test_padding_vertices_are_isolated_and_reduce_to_a_dense_map(name):
