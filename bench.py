@@ -180,7 +180,7 @@ def cpu_port_meshes_per_s(graph_L, sample, threads=None):
     sd = mo.randomize_bn_(mo.init_state_dict(5, 3, [m.shape[0] for m in laps], False), seed=7)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(sample, 17, 5, generator=g)
-    used = best_thread_count(lambda: mo.forward(sd, laps, x[:2], training=False))
+    used = best_thread_count(lambda: mo.forward(sd, laps, x[:min(8, sample)], training=False))
     with torch.no_grad():
         mo.forward(sd, laps, x[:2], training=False)
         t0 = time.perf_counter()
@@ -208,7 +208,7 @@ def run_reference(args):
     sample = max(1, min(args.ref_sample, args.batch))
     g = torch.Generator().manual_seed(1000)
     x = torch.randn(sample, 17, 5, generator=g)
-    cores = best_thread_count(lambda: mo.forward(sd, laps, x[:2], training=False))
+    cores = best_thread_count(lambda: mo.forward(sd, laps, x[:min(8, sample)], training=False))
     with torch.no_grad():
         for _ in range(args.warmup):
             mo.forward(sd, laps, x[:2], training=False)
