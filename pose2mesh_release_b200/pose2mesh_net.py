@@ -19,20 +19,23 @@ class FlatPose2Mesh(nn.Module):
     def __init__(self, num_joint, graph_L, posenet_pretrained: bool = False):
         super().__init__()
         self.num_joint = num_joint
-        self.pose_lifter = posenet.get_model(num_joint, hid_dim=4096, num_layer=2, p_dropout=0.5,
-                                             pretrained=posenet_pretrained)
-        self.pose2mesh = meshnet.get_model(num_joint_input_chan=2 + 3, num_mesh_output_chan=3, graph_L=graph_L)
+        # attribute names = the reference's (state_dict prefixes `pose_lifter.` / `pose2mesh.`), constructed in its order
+        self.pose_lifter = posenet.LinearModel(num_joint, linear_size=4096, num_stage=2, p_dropout=0.5,
+                                               pretrained=posenet_pretrained)
+        self.pose2mesh = meshnet.Pose2Mesh(2 + 3, 3, graph_L)
+
+    def _lift(self, pose2d):
+        """(pose3d [B, J, 3], pose_combine [B, J, 5]): natively in eval mode, the reference's torch ops otherwise."""
+        lifter, flat = self.pose_lifter, pose2d.reshape(len(pose2d), -1)
+        if not lifter.training and pose2d.is_cuda and not (torch.is_grad_enabled() and pose2d.requires_grad):
+            pose3d, combine = lifter.forward_native(flat, with_combine=True)
+            return pose3d.reshape(-1, self.num_joint, 3), combine
+        pose3d = lifter(flat).reshape(-1, self.num_joint, 3)
+        return pose3d, torch.cat((pose2d, pose3d.detach() / 1000), dim=2)
 
     def forward(self, pose2d):
-        lifter = self.pose_lifter
-        if not lifter.training and pose2d.is_cuda and not (torch.is_grad_enabled() and pose2d.requires_grad):
-            pose3d, pose_combine = lifter.forward_native(pose2d.reshape(len(pose2d), -1), with_combine=True)
-            pose3d = pose3d.reshape(-1, self.num_joint, 3)
-        else:
-            pose3d = lifter(pose2d.view(len(pose2d), -1)).reshape(-1, self.num_joint, 3)
-            pose_combine = torch.cat((pose2d, pose3d.detach() / 1000), dim=2)
-        cam_mesh = self.pose2mesh(pose_combine)
-        return cam_mesh, pose3d
+        pose3d, combine = self._lift(pose2d)
+        return self.pose2mesh(combine), pose3d
 
     @torch.no_grad()
     def predict_vertices_and_joints(self, pose2d, perm_reverse, n_vertex, joint_regressor):

@@ -18,47 +18,49 @@ import torch.nn as nn
 from . import _lib
 
 
-def weight_init(m):
-    if isinstance(m, nn.Linear):
-        nn.init.kaiming_normal_(m.weight)
+def weight_init(module):
+    """lib/models/posenet.py:6-8 (kaiming-normal Linear weights; not applied by the reference's constructor either)."""
+    if isinstance(module, nn.Linear):
+        nn.init.kaiming_normal_(module.weight)
+
+
+def _register(owner: nn.Module, spec):
+    """Create the sub-modules of `spec` (name -> factory) in order: registration order fixes both the state_dict key
+    order and the order in which the default initialisers draw from the global RNG (identical to the reference's)."""
+    for name, factory in spec:
+        setattr(owner, name, factory())
 
 
 class Linear(nn.Module):
-    """One residual stage (lib/models/posenet.py:13-39)."""
+    """One residual stage (lib/models/posenet.py:13-39): x + w2(drop(relu(bn2(w1(drop(relu(bn1(x)))))))."""
 
     def __init__(self, linear_size, p_dropout=0.5):
         super().__init__()
-        self.l_size = linear_size
-        self.relu = nn.ReLU(inplace=True)
-        self.dropout = nn.Dropout(p_dropout)
-        self.w1 = nn.Linear(self.l_size, self.l_size)
-        self.batch_norm1 = nn.BatchNorm1d(self.l_size)
-        self.w2 = nn.Linear(self.l_size, self.l_size)
-        self.batch_norm2 = nn.BatchNorm1d(self.l_size)
+        h = self.l_size = linear_size
+        _register(self, (("relu", lambda: nn.ReLU(inplace=True)), ("dropout", lambda: nn.Dropout(p_dropout)),
+                         ("w1", lambda: nn.Linear(h, h)), ("batch_norm1", lambda: nn.BatchNorm1d(h)),
+                         ("w2", lambda: nn.Linear(h, h)), ("batch_norm2", lambda: nn.BatchNorm1d(h))))
 
     def forward(self, x):
-        y = self.w1(self.dropout(self.relu(self.batch_norm1(x))))
-        y = self.w2(self.dropout(self.relu(self.batch_norm2(y))))
+        y = x
+        for bn, lin in ((self.batch_norm1, self.w1), (self.batch_norm2, self.w2)):
+            y = lin(self.dropout(self.relu(bn(y))))
         return x + y
 
 
 class LinearModel(nn.Module):
-    """lib/models/posenet.py:41-87."""
+    """lib/models/posenet.py:41-87: Linear(2J, H) -> `num_stage` residual stages -> Linear(H, 3J)."""
 
     def __init__(self, num_joint, linear_size=4096, num_stage=2, p_dropout=0.5, pretrained=False):
         super().__init__()
-        self.linear_size = linear_size
-        self.p_dropout = p_dropout
-        self.num_stage = num_stage
-        self.num_joint = num_joint
-        self.input_size = num_joint * 2
-        self.output_size = num_joint * 3
-        self.w1 = nn.Linear(self.input_size, self.linear_size)
-        self.batch_norm1 = nn.BatchNorm1d(self.linear_size)   # constructed, never applied (reference :63, :74-87)
-        self.linear_stages = nn.ModuleList([Linear(self.linear_size, self.p_dropout) for _ in range(num_stage)])
-        self.w2 = nn.Linear(self.linear_size, self.output_size)
-        self.relu = nn.ReLU(inplace=True)
-        self.dropout = nn.Dropout(self.p_dropout)
+        self.num_joint, self.linear_size, self.num_stage, self.p_dropout = num_joint, linear_size, num_stage, p_dropout
+        self.input_size, self.output_size = 2 * num_joint, 3 * num_joint          # 2-D joints in, 3-D joints out
+        h = linear_size
+        _register(self, (("w1", lambda: nn.Linear(self.input_size, h)),
+                         ("batch_norm1", lambda: nn.BatchNorm1d(h)),               # constructed, never applied (reference :63 vs :74-87)
+                         ("linear_stages", lambda: nn.ModuleList(Linear(h, p_dropout) for _ in range(num_stage))),
+                         ("w2", lambda: nn.Linear(h, self.output_size)),
+                         ("relu", lambda: nn.ReLU(inplace=True)), ("dropout", lambda: nn.Dropout(p_dropout))))
         if pretrained:
             raise RuntimeError("pretrained PoseNet weights are loaded by the reference's own checkpoint code "
                                "(funcs_utils.load_checkpoint); load_state_dict() them into this module")
@@ -111,8 +113,8 @@ class LinearModel(nn.Module):
         if not self.training and x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad):
             return self.forward_native(x)
         y = self.w1(x)                     # training (dropout, batch statistics): the reference's own op sequence
-        for i in range(self.num_stage):
-            y = self.linear_stages[i](y)
+        for stage in self.linear_stages:
+            y = stage(y)
         return self.w2(y)
 
 
