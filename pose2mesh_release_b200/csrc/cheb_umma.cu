@@ -965,7 +965,7 @@ struct DwParams {
   int meta_stride, max_h1, max_h2;
   const float* g;        // dz [rows, fout_total]
   int fout_total, m_off, m_cols;
-  int chunk0, n_chunk;   // feature chunks [chunk0, chunk0 + n_chunk), n_chunk <= 2
+  int chunk0, n_chunk;   // feature chunks [chunk0, chunk0 + n_chunk), n_chunk <= 2 (n32: <= 4)
   const float* a_scale;  // device scalar (power of two) applied to the gradient tensor before the fp16 split
   float* dw;             // [fout_total, 3*fin], column = f*3 + k  (reference layout), accumulated atomically
   int* status;
@@ -978,6 +978,10 @@ struct DwParams {
   int g_unpool;
   int swap;
   int tma;                 // T1 given, consecutive tiles, V % 128 == 0: the own rows of x and t1 arrive by one 2-D TMA box each
+  int n32;                 // 1: the hi and lo halves of a T block accumulate into the SAME 32 TMEM columns (three N = 32
+                           //    MMAs per K step: g_hi T_hi + g_lo T_hi + g_hi T_lo; the lo half is addressed by starting
+                           //    the MN-major descriptor 64 bytes into the 128-byte swizzle row) -> 12 accumulators of 32
+                           //    columns = FOUR feature chunks per launch: the plain-side tile is split half as often
   CUtensorMap tm_x, tm_t1;
 };
 
@@ -1143,13 +1147,24 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_c
           const int s = ucnt % DW_NS;
           mbar_wait(smem_u32(b_t_full + s), (ucnt / DW_NS) & 1, abort_flag, p.status, 25);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(u * 64);
           const uint64_t dt = make_desc_sw128_mn(smem_u32(ring + s * A_BLOCK_BYTES), A_BLOCK_BYTES);
           const uint64_t dh = make_desc_sw128_mn(g_hi, A_BLOCK_BYTES), dl = make_desc_sw128_mn(g_lo, A_BLOCK_BYTES);
+          if (p.n32) {
+            constexpr uint32_t IDESC32 = make_idesc_f16(TILE_M, 32) | (1u << 15) | (1u << 16);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(u * 32);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 16 mesh rows per K step = 2048 bytes = +128 in the address field
-            umma_f16(d_tmem, dh + ks * 128, dt + ks * 128, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
-            umma_f16(d_tmem, dl + ks * 128, dt + ks * 128, IDESC, 1u);
+            for (int ks = 0; ks < 8; ++ks) {
+              umma_f16(d_tmem, dh + ks * 128, dt + ks * 128, IDESC32, (it > 0 || ks > 0) ? 1u : 0u);  // g_hi T_hi
+              umma_f16(d_tmem, dl + ks * 128, dt + ks * 128, IDESC32, 1u);                              // g_lo T_hi
+              umma_f16(d_tmem, dh + ks * 128, dt + ks * 128 + 4, IDESC32, 1u);                          // g_hi T_lo (+64 B)
+            }
+          } else {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(u * 64);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {  // 16 mesh rows per K step = 2048 bytes = +128 in the address field
+              umma_f16(d_tmem, dh + ks * 128, dt + ks * 128, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(d_tmem, dl + ks * 128, dt + ks * 128, IDESC, 1u);
+            }
           }
           umma_commit(smem_u32(b_t_empty + s));
         }
@@ -1169,8 +1184,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_c
     for (int u = 0; u < n_use; ++u) {
       const int c = u / 3, k = u - 3 * c;
       uint32_t hi[32], lo[32];
-      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 64), hi);
-      tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 64 + 32), lo);
+      if (p.n32) {
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 32), hi);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo[j] = 0u;
+      } else {
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 64), hi);
+        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(u * 64 + 32), lo);
+      }
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -1451,6 +1472,8 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
 }
 
 // debug: P2M_UMMA_TMA=0 stages every row with cp.async (A/B measurements of the TMA own-row loads)
+// debug: P2M_DW_N32=0 keeps separate hi / lo accumulator columns in the swapped dW kernel (two chunks per launch)
+const bool g_dw_n32 = [] { const char* e = std::getenv("P2M_DW_N32"); return !(e && e[0] == '0'); }();
 const bool g_umma_tma = [] { const char* e = std::getenv("P2M_UMMA_TMA"); return !(e && e[0] == '0'); }();
 
 // mode: 0 = fused (X with its 2-hop halo staged, T1 recomputed on chip), 1 = T1 given, 2 = plain GEMM
@@ -1934,9 +1957,10 @@ int launch_dw_kernels(const DevLevel& g, DwParams p, int gathered_width, int pla
   for (int m_off = 0; m_off < plain_width; m_off += 128) {
     p.m_off = m_off;
     p.m_cols = std::min(128, plain_width - m_off);
-    for (int c0 = 0; c0 < total_chunks; c0 += 2) {
+    const int per_launch = p.n32 ? 4 : 2;
+    for (int c0 = 0; c0 < total_chunks; c0 += per_launch) {
       p.chunk0 = c0;
-      p.n_chunk = std::min(2, total_chunks - c0);
+      p.n_chunk = std::min(per_launch, total_chunks - c0);
       kern<<<grid, NUM_THREADS2, smem, s>>>(p);
       P2M_LAUNCH_OK();
     }
@@ -1971,6 +1995,7 @@ int launch_umma_dw(const DevLevel& g, const float* x, int in_unpool, int batch, 
   p.t1 = nullptr;
   p.g_unpool = 0;
   p.swap = 0;
+  p.n32 = 0;
   p.tma = 0;
   std::memset(&p.tm_x, 0, sizeof(p.tm_x));
   std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
@@ -1994,6 +2019,7 @@ int launch_umma_dw_swapped(const DevLevel& g, const float* x, int in_unpool, int
   }
   DwParams p;
   p.tma = 0;
+  p.n32 = g_dw_n32 ? 1 : 0;
   std::memset(&p.tm_x, 0, sizeof(p.tm_x));
   std::memset(&p.tm_t1, 0, sizeof(p.tm_t1));
   p.x = dz;
