@@ -732,15 +732,31 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     uint32_t t1_row[T1_ROWS], t1_e[T1_ROWS];
     uint32_t row0 = 0, row1 = 0, r0e = 0, r1e = 0, ent_a = 0;
     int ptn = 0;
+    // A/B ring cursor (slot, phase parity) kept incrementally, and the four store offsets of this thread's two rows
+    // inside an A block (first / second 8-byte store of each row: odd row groups store lo first, see emit()) —
+    // per-tile constants: the hot loop carries no modulo, division or swizzle arithmetic
+    uint32_t slot = 0, spar = 0;
+    uint32_t so_f[2] = {0, 0}, so_s[2] = {0, 0};
+    const bool odd = (rg & 1) != 0;
+    auto next_slot = [&]() {
+      if (++slot == (uint32_t)NS) {
+        slot = 0;
+        spar ^= 1u;
+      }
+    };
 
     // Stage flat stage g2 (tile it2, chunk c2) into Xs[g2 % XS] (and T1s[g2 % XS] when T1 is given): 16-byte
     // cp.async copies, 8 lanes per 128-byte row, four rows per thread in flight; completion is signalled on
     // x_full[g2 % XS] by cp.async.mbarrier.arrive.noinc.  The target stage was last read in stage g2 - XS, whose
     // end barrier every producer has passed before it gets here.
-    auto issue_stage = [&](int g2) {
-      const int it2 = g2 / n_chunk, c2 = g2 - it2 * n_chunk;
-      const int tile2 = blockIdx.x + it2 * gridDim.x;
-      const int b2 = tile2 / p.P;
+    // (it2, c2) = tile iteration and chunk of flat stage g2; st_b = mesh of the tile being staged, kept incrementally
+    int st_it = -1, st_b = 0;
+    auto issue_stage = [&](int g2, int it2, int c2) {
+      if (it2 != st_it) {  // a new tile: its mesh index (one division per tile instead of two per chunk)
+        st_it = it2;
+        st_b = (int)((blockIdx.x + (unsigned)it2 * gridDim.x) / (unsigned)p.P);
+      }
+      const int b2 = st_b;
       const int m2 = it2 & 1;
       if (c2 == 0) mbar_wait(smem_u32(b_m_full + m2), (it2 >> 1) & 1, abort_flag, p.status, 8);
       const unsigned char* mb2 = meta_s + (size_t)m2 * p.meta_stride;
@@ -786,12 +802,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     };
 
     const int xsh = (p.tma && p.in_unpool) ? 1 : 0;  // TMA-staged unpooled input: staged row = tile row >> 1
-    if (n_stage > 0) issue_stage(0);
+    if (n_stage > 0) issue_stage(0, 0, 0);
+    int it = 0, c = -1;
     for (int g = 0; g < n_stage; ++g) {
-      const int it = g / n_chunk, c = g - it * n_chunk;
+      if (++c == n_chunk) {
+        c = 0;
+        ++it;
+      }
       const int m = it & 1;
       const int xs = g % XS;
-      if (XS == 2 && g + 1 < n_stage) issue_stage(g + 1);  // prefetch: overlaps this stage's work
+      const int c_next = (c + 1 == n_chunk) ? 0 : c + 1, it_next = (c + 1 == n_chunk) ? it + 1 : it;
+      if (XS == 2 && g + 1 < n_stage) issue_stage(g + 1, it_next, c_next);  // prefetch: overlaps this stage's work
       if (tid == 0) trace_ev(p, 0, ptn, 1);
       mbar_wait(smem_u32(b_x_full + xs), (g / XS) & 1, abort_flag, p.status, 9);
       if (tid == 0) trace_ev(p, 0, ptn, 2);
@@ -817,14 +838,25 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         row1 = lds_u16(ord2_a + 2 * (64 + rg));
         r0e = lds_u16(rp_a + 2 * row0) | (lds_u16(rp_a + 2 * row0 + 2) << 16);
         r1e = lds_u16(rp_a + 2 * row1) | (lds_u16(rp_a + 2 * row1 + 2) << 16);
+        if (p.plain) {  // plain GEMM: the thread's rows are the consecutive slots rg and 64 + rg
+          row0 = rg;
+          row1 = 64 + rg;
+        }
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const uint32_t i = ps ? row1 : row0;
+          const uint32_t a_hi = sw128_off(i, q >> 1) + (q & 1) * 8, a_lo = sw128_off(i, 4 + (q >> 1)) + (q & 1) * 8;
+          so_f[ps] = odd ? a_lo : a_hi;
+          so_s[ps] = odd ? a_hi : a_lo;
+        }
       }
       const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
       const uint32_t t1s_q = t1s_a + (t1g ? (uint32_t)(xs * t1_stage_floats * 4) : 0u) + q * 16;
       if (p.plain) {
         // plain GEMM: the staged rows ARE the A operand (scaled into fp16 range if a_scale is given)
-        const int s = ucnt % NS;
-        mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
-        const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
+        const uint32_t s = slot;
+        mbar_wait(smem_u32(b_ab_empty + s), spar ^ 1u, abort_flag, p.status, 10);
+        const uint32_t ablk = ring_a + s * SLOT_BYTES;
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
           const uint32_t i = ps * 64 + rg;
@@ -832,21 +864,20 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
           uint2 hi, lo;
           split4(v, hi, lo);
-          const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
           // the four consecutive rows of a warp share (row & 4), i.e. the 64-byte half their hi parts go to: odd row
           // groups store lo first (selects, see emit()), so that both rows of a half-warp cover different bank halves
-          const bool odd = (rg & 1) != 0;
-          sts_u2(odd ? a_lo : a_hi, odd ? lo : hi);
-          sts_u2(odd ? a_hi : a_lo, odd ? hi : lo);
+          sts_u2(ablk + so_f[ps], odd ? lo : hi);
+          sts_u2(ablk + so_s[ps], odd ? hi : lo);
         }
         fence_async_proxy();
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
         ++ucnt;
+        next_slot();
         producer_barrier();
         if (tid == 0 && p.tma) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the TMA issuer may refill it
         if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-        if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1);  // single stage: refill only after everybody is done
+        if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1, it_next, c_next);  // single stage: refill only after everybody is done
         continue;
       }
       // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows); two rows per
@@ -867,27 +898,24 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       //     block's slot and would otherwise wait for its MMAs).  NS >= 3: ONE generic->async proxy fence for all
       //     three blocks (the fence drains the thread's outstanding shared stores and is expensive); NS < 3: one per
       //     block.  Odd row groups store lo first: a warp then covers both 64-byte halves of its rows per store.
-      const uint32_t u0 = ucnt;
+      const uint32_t slot0 = slot;
       auto emit = [&](const float4& v0, const float4& v1) {
-        const int s = ucnt % NS;
-        mbar_wait(smem_u32(b_ab_empty + s), ((ucnt / NS) & 1) ^ 1, abort_flag, p.status, 10);
-        const uint32_t ablk = ring_a + s * SLOT_BYTES + (q & 1) * 8;
+        const uint32_t s = slot;
+        mbar_wait(smem_u32(b_ab_empty + s), spar ^ 1u, abort_flag, p.status, 10);
+        const uint32_t ablk = ring_a + s * SLOT_BYTES;
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
-          const uint32_t i = ps ? row1 : row0;
           uint2 hi, lo;
           float4 v = ps ? v1 : v0;
           if (p.a_scale != nullptr) {  // backward-data pass: gradients are scaled into fp16's range (power of two)
             v.x *= a_scale; v.y *= a_scale; v.z *= a_scale; v.w *= a_scale;
           }
           split4(v, hi, lo);
-          const uint32_t a_hi = ablk + sw128_off(i, q >> 1), a_lo = ablk + sw128_off(i, 4 + (q >> 1));
           // 64-bit shared stores are served per HALF-warp (two rows here).  Odd row groups store lo first — by
           // selects, not branches: a predicated store would leave each half-warp's wavefront half empty — and the
           // row order pairs rows so that the two 64-byte pieces of a half-warp fall into different bank halves
-          const bool odd = (rg & 1) != 0;
-          sts_u2(odd ? a_lo : a_hi, odd ? lo : hi);
-          sts_u2(odd ? a_hi : a_lo, odd ? hi : lo);
+          sts_u2(ablk + so_f[ps], odd ? lo : hi);
+          sts_u2(ablk + so_s[ps], odd ? hi : lo);
         }
         if (NS < 3) {
           fence_async_proxy();
@@ -895,6 +923,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
         }
         ++ucnt;
+        next_slot();
       };
       if (NS < 3) {
         const float4 x0 = lds_f4(xs_q + (row0 >> xsh) * 128), x1 = lds_f4(xs_q + (row1 >> xsh) * 128);
@@ -926,7 +955,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         __syncwarp();
         if ((tid & 31) == 0) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) mbar_arrive(smem_u32(b_ab_full + (u0 + k) % NS));  // one arrival per warp
+          for (int k = 0; k < 3; ++k) mbar_arrive(smem_u32(b_ab_full + (slot0 + k) % NS));  // one arrival per warp
         }
       }
       if (tid == 0) trace_ev(p, 0, ptn, 7);
@@ -934,7 +963,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (tid == 0) trace_ev(p, 0, ptn, 8);
       if (tid == 0 && p.tma) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the TMA issuer may refill it
       if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-      if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1);  // single stage: refill only after everybody is done
+      if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1, it_next, c_next);  // single stage: refill only after everybody is done
     }
   }
   tc_fence_before();
