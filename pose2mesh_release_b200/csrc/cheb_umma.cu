@@ -182,6 +182,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 // explicit shared-window accesses (32-bit addresses): keeps the hot loops on LDS/STS instead of generic LD/ST
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   float4 v;
@@ -215,6 +216,10 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
 // trips per four entries instead of two per entry (rows have <= 14 entries).  (Fetching each entry once per row and
 // passing it round the row's 8 lanes with width-8 shuffles was measured in round 2: 15 % SLOWER — shuffles run on
 // the same MIO/shared-memory pipe that bounds these kernels.)
+// T2 = 2 (L~ T1) - X, one FMA per element (2 g is exact, so this rounds like the subtraction of the doubled value)
+__device__ __forceinline__ float4 cheb_t2(const float4& g, const float4& x) {
+  return make_float4(fmaf(2.f, g.x, -x.x), fmaf(2.f, g.y, -x.y), fmaf(2.f, g.z, -x.z), fmaf(2.f, g.w, -x.w));
+}
 __device__ __forceinline__ float4 gather_row4(uint32_t ent, uint32_t e, uint32_t e1, uint32_t rows_q) {
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
   for (; e + 3 < e1; e += 4) {
@@ -599,9 +604,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           }
         }
       }
-      // a tile lasts ~10 us and the accumulator is double-buffered: coarse polling keeps these four warps out of the
-      // producers' issue slots (at 200 ns their polls were 12 % of the kernel's executed instructions)
-      mbar_wait_relaxed<800>(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
+      // only the first epilogue warp polls the mbarrier, the other three sleep in a hardware barrier until it has seen
+      // the accumulator (four polling warps were 12 % of the kernel's executed instructions: a suspended try_wait wakes
+      // on every mbarrier event of the CTA, i.e. every ~100 cycles here)
+      if (warp == W_EPI0) mbar_wait_relaxed(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
+      epilogue_barrier();
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 1);
       tc_fence_after();
       if (N == 64 && p.head_z != nullptr) {
@@ -773,7 +780,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       const int xs2 = g2 % XS;
       // sbase already points at the mesh's first row (64-bit address math once per stage); the row offset of a staged
       // slot fits 32 bits.  Empty slots (-1) are zero-filled by the copy itself (src-size 0): no branch per row.
-      auto stage_rows = [&](uint32_t dbase, const float* sbase, int first, int n_rows, int sh) {
+      const uint32_t fin_bytes = (uint32_t)p.fin * 4u;
+      auto stage_rows = [&](uint32_t dbase, const char* sbase, int first, int n_rows, int sh) {
         for (int i0 = first + rg; i0 < n_rows; i0 += 256) {
           int v[4];
 #pragma unroll
@@ -781,14 +789,18 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (v[u] != -2) {
-              const uint32_t off = ((uint32_t)max(v[u], 0) >> sh) * (uint32_t)p.fin;
-              cp_async16_zfill(dbase + (i0 + 64 * u) * 128, sbase + off, v[u] >= 0 ? 16u : 0u);
+              // one 32 x 32 -> 64-bit multiply-add per row (a row's byte offset inside a mesh fits 32 bits)
+              const uint32_t srow = (uint32_t)max(v[u], 0) >> sh;
+              cp_async16_zfill(dbase + (i0 + 64 * u) * 128, sbase + (uint64_t)srow * (uint64_t)fin_bytes,
+                               v[u] >= 0 ? 16u : 0u);
             }
           }
         }
       };
       const uint32_t xbar = smem_u32(b_x_full + xs2);
-      const float* t1_mesh = t1g ? p.t1 + mesh_row0 * p.fin + c2 * FC + q * 4 : nullptr;
+      const char* t1_mesh = reinterpret_cast<const char*>(t1g ? p.t1 + mesh_row0 * p.fin + c2 * FC + q * 4 : nullptr);
+      const char* x_mesh =
+          reinterpret_cast<const char*>(p.x + (mesh_row0 >> (p.in_unpool ? 1 : 0)) * p.fin + c2 * FC + q * 4);
       if (tid == 0) trace_ev(p, 0, ptn, 20);
       if (p.tma) {
         // own rows: one TMA box per operand, issued by warp 17 and landing asynchronously (the cp.async route blocks
@@ -798,9 +810,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       } else {
         if (t1g)
           stage_rows(smem_u32(T1s + xs2 * t1_stage_floats) + q * 16, t1_mesh, 0, hdr2->h1, 0);
-        stage_rows(smem_u32(Xs + xs2 * xs_stage_floats) + q * 16,
-                   p.x + (mesh_row0 >> (p.in_unpool ? 1 : 0)) * p.fin + c2 * FC + q * 4, 0,
-                   (p.plain || t1g) ? TILE_M : hdr2->h2, p.in_unpool ? 1 : 0);
+        stage_rows(smem_u32(Xs + xs2 * xs_stage_floats) + q * 16, x_mesh, 0, (p.plain || t1g) ? TILE_M : hdr2->h2,
+                   p.in_unpool ? 1 : 0);
         if (tid == 0) mbar_arrive(xbar);
       }
       if (tid == 0) trace_ev(p, 0, ptn, 21);
@@ -942,8 +953,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
         const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
         if (tid == 0) trace_ev(p, 0, ptn, 6);
-        emit(make_float4(2.f * g0.x - x0.x, 2.f * g0.y - x0.y, 2.f * g0.z - x0.z, 2.f * g0.w - x0.w),
-             make_float4(2.f * g1.x - x1.x, 2.f * g1.y - x1.y, 2.f * g1.z - x1.z, 2.f * g1.w - x1.w));
+        emit(cheb_t2(g0, x0),
+             cheb_t2(g1, x1));
       } else {
         // deep ring: gather first, then the three blocks back to back (measured faster than the early X/T1 emit:
         // the gather then overlaps the previous chunk's tail instead of this chunk's own stores)
@@ -954,8 +965,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         if (tid == 0) trace_ev(p, 0, ptn, 6);
         emit(x0, x1);
         emit(t10, t11);
-        emit(make_float4(2.f * g0.x - x0.x, 2.f * g0.y - x0.y, 2.f * g0.z - x0.z, 2.f * g0.w - x0.w),
-             make_float4(2.f * g1.x - x1.x, 2.f * g1.y - x1.y, 2.f * g1.z - x1.z, 2.f * g1.w - x1.w));
+        emit(cheb_t2(g0, x0),
+             cheb_t2(g1, x1));
       }
       if (NS >= 3) {
         fence_async_proxy();
@@ -1344,8 +1355,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_dw_umma(const __grid_c
           tv[1][0] = lds_f4(t1s_q + row0 * 128);
           tv[1][1] = lds_f4(t1s_q + row1 * 128);
           const float4 a = tv[0][0], c2 = tv[0][1];
-          tv[2][0] = make_float4(2.f * g0.x - a.x, 2.f * g0.y - a.y, 2.f * g0.z - a.z, 2.f * g0.w - a.w);
-          tv[2][1] = make_float4(2.f * g1.x - c2.x, 2.f * g1.y - c2.y, 2.f * g1.z - c2.z, 2.f * g1.w - c2.w);
+          tv[2][0] = cheb_t2(g0, a);
+          tv[2][1] = cheb_t2(g1, c2);
           if (p.swap) {  // the gathered side is the gradient: into fp16's range before the split
 #pragma unroll
             for (int k = 0; k < 3; ++k)
