@@ -433,8 +433,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       mbar_init(smem_u32(b_ab_empty + s), 1);
     }
     for (int s = 0; s < XS; ++s) {
-      mbar_init(smem_u32(b_x_full + s), W_PROD * 32 + 1);  // every producer thread (cp.async.mbarrier.arrive.noinc)
-                                                           // + thread 0 once more (expect_tx of the TMA loads)
+      mbar_init(smem_u32(b_x_full + s), N_XLOAD * 32 + 1);  // every loader thread (cp.async.mbarrier.arrive.noinc)
+                                                            // + one expect_tx (TMA) / plain arrival of loader thread 32
       mbar_init(smem_u32(b_x_empty + s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -465,39 +465,90 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= W_XLOAD && warp < W_XLOAD + N_XLOAD) {
-    // ------------------------------------------------------------ tile-metadata loader (one thread, cp.async.bulk)
-    // (the X / T1 rows themselves are staged by the producers: two dedicated loader warps could not keep up once the
-    //  first sparse product moved out of this kernel — 16 spinning producer warps starve them of issue slots)
-    if (tid == W_XLOAD * 32 && p.apack == nullptr) {
+    // ------------------------------------------------------------ loaders (two warps): tile metadata, own rows, halo rows
+    // Per stage (tile, 32-feature chunk) they bring in what the producers read: the tile's metadata blob (thread 0,
+    // cp.async.bulk, one tile ahead), the own rows of X / T1 (one 2-D TMA box each where the tile is a run of
+    // consecutive rows — thread 32), and every other staged row with 16-byte cp.async copies (8 lanes per 128-byte row,
+    // all 64 threads): the T1 rows of the 1-hop halo, or all rows where the tile is an index list / no T1 is given.
+    // A stage needs ~60 warp-level copies; issued by the 16 producer warps (round 2 until this change) every warp paid
+    // the whole preamble for its one to four rows — a fifth of the producers' instruction stream per chunk.
+    if (p.apack == nullptr) {
+      const int lt = tid - W_XLOAD * 32;  // 0..63
+      const int lq = lt & 7, lrg = lt >> 3;
       const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int pat = (blockIdx.x + it * gridDim.x) % p.P;
-        const int m = it & 1;
-        mbar_wait_relaxed(smem_u32(b_m_empty + m), ((it >> 1) & 1) ^ 1, abort_flag, p.status, 1);
+      if (lt == 32 && p.tma) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_x)) : "memory");
+        if (t1g) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_t1)) : "memory");
+      }
+      auto fetch_meta = [&](int itf) {  // thread 0: blob of this CTA's tile number itf into buffer itf & 1
+        const int pat = (blockIdx.x + itf * gridDim.x) % p.P;
+        const int m = itf & 1;
+        mbar_wait_relaxed(smem_u32(b_m_empty + m), ((itf >> 1) & 1) ^ 1, abort_flag, p.status, 1);
         const int mbytes = p.meta_bytes[pat];
         mbar_arrive_expect_tx(smem_u32(b_m_full + m), mbytes);
         bulk_g2s(smem_u32(meta_s + (size_t)m * p.meta_stride), p.meta + (size_t)pat * p.meta_stride, mbytes,
                  smem_u32(b_m_full + m));
-      }
-    } else if (tid == (W_XLOAD + 1) * 32 && p.tma) {
-      // ---------------------------------------------------------- own-row TMA issuer (one thread of warp 17)
-      // Issuing the two tensor-map loads of a stage costs the issuing warp ~1.5 k cycles (tools/umma_trace.py, round
-      // 2): done by producer thread 0 that delay sat on every chunk's critical path (all 16 producer warps meet at
-      // the chunk barrier).  This otherwise idle warp only needs the stage to be free (x_empty, arrived by producer
-      // thread 0 after the chunk barrier) — tile and chunk of a stage follow from its index.
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_x)) : "memory");
-      if (t1g) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_t1)) : "memory");
-      const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      const int n_stage = my_tiles * n_chunk;
-      for (int g2 = 0; g2 < n_stage; ++g2) {
-        const int xs2 = g2 % XS;
-        mbar_wait_relaxed(smem_u32(b_x_empty + xs2), ((g2 / XS) & 1) ^ 1, abort_flag, p.status, 11);
-        const int it2 = g2 / n_chunk, c2 = g2 - it2 * n_chunk;
-        const int own0 = (blockIdx.x + it2 * gridDim.x) * TILE_M;  // V is a multiple of 128: tiles never straddle meshes
-        const uint32_t xbar = smem_u32(b_x_full + xs2);
-        mbar_arrive_expect_tx(xbar, (p.in_unpool ? TILE_M / 2 : TILE_M) * 128 + (t1g ? TILE_M * 128 : 0));
-        tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
-        if (t1g) tma_load_2d(smem_u32(T1s + xs2 * t1_stage_floats), &p.tm_t1, c2 * FC, own0, xbar);
+      };
+      if (lt == 0 && my_tiles > 0) fetch_meta(0);
+      const uint32_t fin_bytes = (uint32_t)p.fin * 4u;
+      const int sh = p.in_unpool ? 1 : 0;
+      int g2 = 0;
+      int ltn = 0;
+      for (int it2 = 0; it2 < my_tiles; ++it2) {
+        const int tile2 = blockIdx.x + it2 * gridDim.x;
+        const long long mesh_row0 = (long long)(tile2 / p.P) * p.V;
+        const int m2 = it2 & 1;
+        mbar_wait_relaxed(smem_u32(b_m_full + m2), (it2 >> 1) & 1, abort_flag, p.status, 8);
+        const unsigned char* mb2 = meta_s + (size_t)m2 * p.meta_stride;
+        const TileHeader* hdr2 = reinterpret_cast<const TileHeader*>(mb2);
+        const int* halo = reinterpret_cast<const int*>(mb2 + hdr2->off_halo);
+        const int h1 = hdr2->h1, h2 = hdr2->h2;
+        for (int c2 = 0; c2 < n_chunk; ++c2, ++g2) {
+          const int xs2 = g2 % XS;
+          mbar_wait_relaxed(smem_u32(b_x_empty + xs2), ((g2 / XS) & 1) ^ 1, abort_flag, p.status, 11);
+          if (lt == 0) trace_ev(p, 4, ltn, 1);
+          const uint32_t xbar = smem_u32(b_x_full + xs2);
+          // a row's byte offset inside its mesh fits 32 bits: one 32 x 32 -> 64-bit multiply-add per row; empty slots
+          // (-1) are zero-filled by the copy itself (src-size 0)
+          auto stage_rows = [&](uint32_t dbase, const char* sbase, int first, int n_rows, int shift) {
+            for (int i0 = first + lrg; i0 < n_rows; i0 += 32) {
+              int v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) v[u] = (i0 + 8 * u < n_rows) ? halo[i0 + 8 * u] : -2;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (v[u] != -2) {
+                  const uint32_t srow = (uint32_t)max(v[u], 0) >> shift;
+                  cp_async16_zfill(dbase + (i0 + 8 * u) * 128, sbase + (uint64_t)srow * (uint64_t)fin_bytes,
+                                   v[u] >= 0 ? 16u : 0u);
+                }
+              }
+            }
+          };
+          const char* t1_mesh =
+              reinterpret_cast<const char*>(t1g ? p.t1 + mesh_row0 * p.fin + c2 * FC + lq * 4 : nullptr);
+          const char* x_mesh = reinterpret_cast<const char*>(p.x + (mesh_row0 >> sh) * p.fin + c2 * FC + lq * 4);
+          const uint32_t t1_dst = smem_u32(T1s + xs2 * t1_stage_floats) + lq * 16;
+          const uint32_t x_dst = smem_u32(Xs + xs2 * xs_stage_floats) + lq * 16;
+          if (p.tma) {
+            if (lt == 32) {
+              const int own0 = tile2 * TILE_M;  // V is a multiple of 128: tiles never straddle meshes
+              mbar_arrive_expect_tx(xbar, (p.in_unpool ? TILE_M / 2 : TILE_M) * 128 + (t1g ? TILE_M * 128 : 0));
+              tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
+              if (t1g) tma_load_2d(smem_u32(T1s + xs2 * t1_stage_floats), &p.tm_t1, c2 * FC, own0, xbar);
+            }
+            if (t1g) stage_rows(t1_dst, t1_mesh, TILE_M, h1, 0);  // only the halo rows are left
+          } else {
+            if (t1g) stage_rows(t1_dst, t1_mesh, 0, h1, 0);
+            stage_rows(x_dst, x_mesh, 0, (p.plain || t1g) ? TILE_M : h2, sh);
+            if (lt == 32) mbar_arrive(xbar);
+          }
+          cp_async_arrive_noinc(xbar);  // this thread's arrival once its copies have landed
+          if (lt == 0) trace_ev(p, 4, ltn, 2);
+          // next tile's metadata: its buffer was last read for tile it2 - 1, which the producers have left by the time
+          // the second chunk of this tile could be staged (single-chunk layers: by the time its only chunk could)
+          if (lt == 0 && c2 == (n_chunk > 1 ? 1 : 0) && it2 + 1 < my_tiles) fetch_meta(it2 + 1);
+        }
       }
     }
   } else if (warp == W_BLOAD) {
@@ -759,68 +810,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       }
     };
 
-    // Stage flat stage g2 (tile it2, chunk c2) into Xs[g2 % XS] (and T1s[g2 % XS] when T1 is given): 16-byte
-    // cp.async copies, 8 lanes per 128-byte row, four rows per thread in flight; completion is signalled on
-    // x_full[g2 % XS] by cp.async.mbarrier.arrive.noinc.  The target stage was last read in stage g2 - XS, whose
-    // end barrier every producer has passed before it gets here.
-    // (it2, c2) = tile iteration and chunk of flat stage g2; st_b = mesh of the tile being staged, kept incrementally
-    int st_it = -1, st_b = 0;
-    auto issue_stage = [&](int g2, int it2, int c2) {
-      if (it2 != st_it) {  // a new tile: its mesh index (one division per tile instead of two per chunk)
-        st_it = it2;
-        st_b = (int)((blockIdx.x + (unsigned)it2 * gridDim.x) / (unsigned)p.P);
-      }
-      const int b2 = st_b;
-      const int m2 = it2 & 1;
-      if (c2 == 0) mbar_wait(smem_u32(b_m_full + m2), (it2 >> 1) & 1, abort_flag, p.status, 8);
-      const unsigned char* mb2 = meta_s + (size_t)m2 * p.meta_stride;
-      const TileHeader* hdr2 = reinterpret_cast<const TileHeader*>(mb2);
-      const int* halo = reinterpret_cast<const int*>(mb2 + hdr2->off_halo);
-      const long long mesh_row0 = (long long)b2 * p.V;
-      const int xs2 = g2 % XS;
-      // sbase already points at the mesh's first row (64-bit address math once per stage); the row offset of a staged
-      // slot fits 32 bits.  Empty slots (-1) are zero-filled by the copy itself (src-size 0): no branch per row.
-      const uint32_t fin_bytes = (uint32_t)p.fin * 4u;
-      auto stage_rows = [&](uint32_t dbase, const char* sbase, int first, int n_rows, int sh) {
-        for (int i0 = first + rg; i0 < n_rows; i0 += 256) {
-          int v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = (i0 + 64 * u < n_rows) ? halo[i0 + 64 * u] : -2;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (v[u] != -2) {
-              // one 32 x 32 -> 64-bit multiply-add per row (a row's byte offset inside a mesh fits 32 bits)
-              const uint32_t srow = (uint32_t)max(v[u], 0) >> sh;
-              cp_async16_zfill(dbase + (i0 + 64 * u) * 128, sbase + (uint64_t)srow * (uint64_t)fin_bytes,
-                               v[u] >= 0 ? 16u : 0u);
-            }
-          }
-        }
-      };
-      const uint32_t xbar = smem_u32(b_x_full + xs2);
-      const char* t1_mesh = reinterpret_cast<const char*>(t1g ? p.t1 + mesh_row0 * p.fin + c2 * FC + q * 4 : nullptr);
-      const char* x_mesh =
-          reinterpret_cast<const char*>(p.x + (mesh_row0 >> (p.in_unpool ? 1 : 0)) * p.fin + c2 * FC + q * 4);
-      if (tid == 0) trace_ev(p, 0, ptn, 20);
-      if (p.tma) {
-        // own rows: one TMA box per operand, issued by warp 17 and landing asynchronously (the cp.async route blocks
-        // the issuing warps once the load queue is full, i.e. for most of the copy); only the halo rows are left
-        if (t1g)
-          stage_rows(smem_u32(T1s + xs2 * t1_stage_floats) + q * 16, t1_mesh, TILE_M, hdr2->h1, 0);
-      } else {
-        if (t1g)
-          stage_rows(smem_u32(T1s + xs2 * t1_stage_floats) + q * 16, t1_mesh, 0, hdr2->h1, 0);
-        stage_rows(smem_u32(Xs + xs2 * xs_stage_floats) + q * 16, x_mesh, 0, (p.plain || t1g) ? TILE_M : hdr2->h2,
-                   p.in_unpool ? 1 : 0);
-        if (tid == 0) mbar_arrive(xbar);
-      }
-      if (tid == 0) trace_ev(p, 0, ptn, 21);
-      cp_async_arrive_noinc(xbar);
-      if (tid == 0) trace_ev(p, 0, ptn, 22);
-    };
-
     const int xsh = (p.tma && p.in_unpool) ? 1 : 0;  // TMA-staged unpooled input: staged row = tile row >> 1
-    if (n_stage > 0) issue_stage(0, 0, 0);
     int it = 0, c = -1;
     for (int g = 0; g < n_stage; ++g) {
       if (++c == n_chunk) {
@@ -829,13 +819,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       }
       const int m = it & 1;
       const int xs = g % XS;
-      const int c_next = (c + 1 == n_chunk) ? 0 : c + 1, it_next = (c + 1 == n_chunk) ? it + 1 : it;
-      if (XS == 2 && g + 1 < n_stage) issue_stage(g + 1, it_next, c_next);  // prefetch: overlaps this stage's work
       if (tid == 0) trace_ev(p, 0, ptn, 1);
       mbar_wait(smem_u32(b_x_full + xs), (g / XS) & 1, abort_flag, p.status, 9);
       if (tid == 0) trace_ev(p, 0, ptn, 2);
 
       if (c == 0) {  // per-tile bookkeeping: which rows this thread owns and where their CSR rows start/end
+        mbar_wait(smem_u32(b_m_full + m), (it >> 1) & 1, abort_flag, p.status, 8);  // (long complete: the loaders read it)
         const unsigned char* mb = meta_s + (size_t)m * p.meta_stride;
         const TileHeader* hdr = reinterpret_cast<const TileHeader*>(mb);
         const uint32_t mb_a = smem_u32(mb);
@@ -893,9 +882,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         ++ucnt;
         next_slot();
         producer_barrier();
-        if (tid == 0 && p.tma) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the TMA issuer may refill it
+        if (tid == 0) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the loaders may refill it
         if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-        if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1, it_next, c_next);  // single stage: refill only after everybody is done
         continue;
       }
       // (1) T1 = L~ X on the tile rows and their 1-hop halo (local CSR columns = staged X rows); two rows per
@@ -979,9 +967,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (tid == 0) trace_ev(p, 0, ptn, 7);
       producer_barrier();  // everybody is done with Xs[xs] and T1s
       if (tid == 0) trace_ev(p, 0, ptn, 8);
-      if (tid == 0 && p.tma) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the TMA issuer may refill it
+      if (tid == 0) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the loaders may refill it
       if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
-      if (XS == 1 && g + 1 < n_stage) issue_stage(g + 1, it_next, c_next);  // single stage: refill only after everybody is done
     }
   }
   tc_fence_before();

@@ -300,6 +300,12 @@ int conv_linear(p2m_model* m, const Layer& L, int B, const float* x, int in_unpo
     P2M_TRY(launch_umma_pack_weights(w_ref, L.fin, L.fout, wpack, s));
     UmmaConvArgs a;
     a.trace = m->trace;
+    if (a.trace != nullptr) {  // trace builds only: P2M_TRACE_V / P2M_TRACE_UNPOOL pick the layer whose launch is logged
+      const char* tv = getenv("P2M_TRACE_V");
+      const char* tu = getenv("P2M_TRACE_UNPOOL");
+      const char* tf = getenv("P2M_TRACE_FOUT");
+      if ((tv && atoi(tv) != L.V) || (tu && atoi(tu) != in_unpool) || (tf && atoi(tf) != L.fout)) a.trace = nullptr;
+    }
     a.head_wt = head_wt;
     a.head_z = head_z;
     // Padding-vertex elision (DevLevel::n_iso): connected rows through the conv on index-list tiles, isolated rows
