@@ -378,6 +378,10 @@ __device__ __forceinline__ void trace_ev(const KParams&, int, int&, int) {}
 constexpr int W_PROD = 16;
 constexpr int W_XLOAD = 16, N_XLOAD = 2, W_BLOAD = 18, W_MMA = 19, W_EPI0 = 20;
 constexpr int NUM_THREADS2 = 24 * 32;
+constexpr int REGS_LAUNCH = 80, REGS_UTIL = 56, REGS_EPI = 104;  // setmaxnreg targets per warpgroup (see the kernel)
+// setmaxnreg.inc draws on the pool the CTA's own setmaxnreg.dec filled: requests beyond it would spin forever
+static_assert(128 * (REGS_EPI - REGS_LAUNCH) <= 128 * (REGS_LAUNCH - REGS_UTIL), "register pool balance");
+static_assert(W_XLOAD % 4 == 0 && W_EPI0 % 4 == 0 && W_EPI0 - W_XLOAD == 4, "setmaxnreg works on aligned warpgroups");
 
 // RM = 1: the residual is the 2:1 channel resampling of a 2N-wide tensor (F.interpolate(linear, align_corners=False)
 // from 2N to N channels is the mean of channel pairs: src = 2j + 0.5), fetched as two 16-byte loads per four outputs
@@ -464,6 +468,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register split by warpgroup (the kernel is launched with 80 per thread: 768 x 80 = 60 K of the SM's 64 K): the
+  // utility warpgroup (loaders, weight loader, MMA issuer) hands back half of its share and the epilogue warpgroup takes
+  // exactly that (120 per thread) — enough to keep a sub-slab of residual pieces, its vertex ids and affine
+  // coefficients in registers instead of re-reading them from shared memory per piece.  The producers stay at 80.
+  // (each budget is set at the top of its own region: after a join ptxas has to assume the smallest one)
+  if (warp >= W_XLOAD && warp < W_EPI0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_UTIL));
   if (warp >= W_XLOAD && warp < W_XLOAD + N_XLOAD) {
     // ------------------------------------------------------------ loaders (two warps): tile metadata, own rows, halo rows
     // Per stage (tile, 32-feature chunk) they bring in what the producers read: the tile's metadata blob (thread 0,
@@ -609,7 +620,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         umma_commit(smem_u32(b_acc_full + as));
       }
     }
+  }
   } else if (warp >= W_EPI0) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> (transpose) -> HBM
     // tcgen05.ld hands every thread one accumulator ROW; storing that directly makes each warp-wide 16-byte store
     // touch 32 different lines.  The rows are therefore transposed through a small per-warp staging buffer so that
@@ -620,6 +633,16 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     constexpr int RPI = 32 / CPR;           // rows covered by one warp-wide 16-byte access
     const uint32_t stg = smem_u32(epi_stage) + (uint32_t)(warp - W_EPI0) * (32 * EC * 4);
     const int prow = lane / CPR, pc = lane % CPR;
+    constexpr int NP = 32 / RPI;              // phase-2 rows (pieces) per thread and sub-slab
+    constexpr int NSW = (EC == 32) ? 2 : 1;   // distinct column chunks a thread touches per sub-slab (swizzle: row & 7)
+    const bool res_reg = (PAIR || (p.ep.res != nullptr && p.res_identity)) && !(N == 64 && p.head_z != nullptr);
+    int colk[NSW];  // column (inside a sub-slab) of the 16-byte chunk this thread handles for rows of swizzle class k
+#pragma unroll
+    for (int k = 0; k < NSW; ++k) {
+      const int rr = k * RPI + prow;
+      const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
+      colk[k] = (int)(((uint32_t)pc ^ sw2) << 2);
+    }
     const uint32_t sw1 = (EC == 32) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
     int it = 0;
     int etn = 0;
@@ -641,6 +664,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         own_w[lane] = v;
         __syncwarp();
       }
+      // vertex id of each of this thread's NP phase-2 rows, kept in registers for the whole tile (every shared-memory
+      // instruction saved here matters: the epilogue warps queue behind the producers on the same LSU/MIO pipe, and on
+      // the layers with a residual their ~250 instructions per tile made them the slowest role — tools/umma_trace_model.py)
+      int own_v[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) own_v[i] = own_w[i * RPI + prow];
       if (p.ep.res != nullptr) {
         // pull this tile's residual rows into L2 while its main loop is still running: the reads below then pay
         // an L2 hit instead of a DRAM round trip per batch
@@ -653,6 +682,32 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
             const long long r = mesh0 + vtx;
             prefetch_l2(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + (p.apack != nullptr ? ecol0 : 0) + ln * 32);
           }
+        }
+      }
+      // Residual pieces that are added straight from registers (identity / pair-mean): rv[][] always holds the pieces
+      // of the NEXT 32 columns — the first 32 are issued here, before the accumulator wait, and each piece is re-issued
+      // for the column 32 further on as soon as it has been consumed, so a piece has a whole 32-column slab of time to
+      // arrive (one batch of four at a time exposed ~8 L2 round trips per tile).
+      uint32_t res_off[NP];  // float index of the residual row of piece i (row * res_F < 2^32)
+      float4 rv[32 / EC][NP];
+      auto res_piece = [&](int i, int n) -> float4 {
+        if (own_v[i] < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* row = p.ep.res + (size_t)res_off[i];
+        if (PAIR) {
+          const float4* src = reinterpret_cast<const float4*>(row + 2 * n);
+          const float4 a = __ldg(src), b = __ldg(src + 1);
+          return make_float4(0.5f * a.x + 0.5f * a.y, 0.5f * a.z + 0.5f * a.w, 0.5f * b.x + 0.5f * b.y,
+                             0.5f * b.z + 0.5f * b.w);
+        }
+        return __ldg(reinterpret_cast<const float4*>(row + ecol0 + n));
+      };
+      if (res_reg) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const long long r = mesh0 + max(own_v[i], 0);
+          res_off[i] = (uint32_t)((p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F);
+#pragma unroll
+          for (int h = 0; h < 32 / EC; ++h) rv[h][i] = res_piece(i, h * EC + colk[i & (NSW - 1)]);
         }
       }
       // only the first epilogue warp polls the mbarrier, the other three sleep in a hardware barrier until it has seen
@@ -707,73 +762,42 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           __syncwarp();
           // phase 2: lane = (row inside an RPI-row group, 16-byte chunk).  The residual pieces of the whole slice
           // are fetched up front (read-only path): behind the y stores the compiler could not batch them.
-          constexpr int IB = 4;  // row groups per batch (bounds the registers held by the residual pieces)
+          // the thread's output columns of this sub-slab (two alternating 16-byte chunks for EC = 32, one for EC = 16)
+          // and their affine coefficients: fetched once per sub-slab instead of once per piece
+          const int cbh = cb + h * EC;
+          float4 mu_k[NSW], ad_k[NSW];
 #pragma unroll
-          for (int i0 = 0; i0 < 32 / RPI; i0 += IB) {
-            float4 rv[IB];
-            if (PAIR) {
+          for (int k = 0; k < NSW; ++k) {
+            mu_k[k] = *reinterpret_cast<const float4*>(ep_mul + cbh + colk[k]);
+            ad_k[k] = *reinterpret_cast<const float4*>(ep_add + cbh + colk[k]);
+          }
 #pragma unroll
-              for (int i = 0; i < IB; ++i) {
-                const int rr = (i0 + i) * RPI + prow;
-                const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
-                const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
-                const int vtx = own_w[rr];
-                const long long r = mesh0 + vtx;
-                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (vtx >= 0) {
-                  const float4* src =
-                      reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + 2 * n);
-                  const float4 a = __ldg(src), b = __ldg(src + 1);
-                  rv[i] = make_float4(0.5f * a.x + 0.5f * a.y, 0.5f * a.z + 0.5f * a.w, 0.5f * b.x + 0.5f * b.y,
-                                      0.5f * b.z + 0.5f * b.w);
+          for (int i = 0; i < NP; ++i) {
+            const int rr = i * RPI + prow;
+            const int n = cbh + colk[i & (NSW - 1)];
+            const float4 a = lds_f4(stg + rr * (EC * 4) + (pc << 4));
+            const int vtx = own_v[i];
+            if (vtx >= 0) {
+              const float4 mu = mu_k[i & (NSW - 1)], ad = ad_k[i & (NSW - 1)];
+              float o[4] = {fmaf(a.x, mu.x, ad.x), fmaf(a.y, mu.y, ad.y), fmaf(a.z, mu.z, ad.z), fmaf(a.w, mu.w, ad.w)};
+              if (p.ep.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+              }
+              const long long r = mesh0 + vtx;
+              if (res_reg) {
+                o[0] += rv[h][i].x; o[1] += rv[h][i].y; o[2] += rv[h][i].z; o[3] += rv[h][i].w;
+              } else if (p.ep.res != nullptr) {
+                const float* res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float l = __ldg(p.ep.lam + n + e);
+                  o[e] += (1.f - l) * __ldg(res_row + __ldg(p.ep.i0 + n + e)) + l * __ldg(res_row + __ldg(p.ep.i1 + n + e));
                 }
               }
-            } else if (p.ep.res != nullptr && p.res_identity) {
-#pragma unroll
-              for (int i = 0; i < IB; ++i) {
-                const int rr = (i0 + i) * RPI + prow;
-                const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
-                const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
-                const int vtx = own_w[rr];
-                const long long r = mesh0 + vtx;
-                rv[i] = (vtx >= 0)
-                            ? __ldg(reinterpret_cast<const float4*>(p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F + ecol0 + n))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
+              *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + ecol0 + n) = make_float4(o[0], o[1], o[2], o[3]);
             }
-#pragma unroll
-            for (int i = 0; i < IB; ++i) {
-              const int rr = (i0 + i) * RPI + prow;
-              const uint32_t sw2 = (EC == 32) ? (uint32_t)(rr & 7) : (uint32_t)((rr >> 1) & 3);
-              const int n = cb + h * EC + (int)(((uint32_t)pc ^ sw2) << 2);
-              const float4 a = lds_f4(stg + rr * (EC * 4) + (pc << 4));
-              const int vtx = own_w[rr];
-              if (vtx >= 0) {
-                const float4 mu = *reinterpret_cast<const float4*>(ep_mul + n);
-                const float4 ad = *reinterpret_cast<const float4*>(ep_add + n);
-                float o[4] = {fmaf(a.x, mu.x, ad.x), fmaf(a.y, mu.y, ad.y), fmaf(a.z, mu.z, ad.z), fmaf(a.w, mu.w, ad.w)};
-                if (p.ep.relu) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-                }
-                const long long r = mesh0 + vtx;
-                if (PAIR) {
-                  o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
-                } else if (p.ep.res != nullptr) {
-                  if (p.res_identity) {
-                    o[0] += rv[i].x; o[1] += rv[i].y; o[2] += rv[i].z; o[3] += rv[i].w;
-                  } else {
-                    const float* res_row = p.ep.res + (p.ep.res_unpool ? (r >> 1) : r) * p.ep.res_F;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float l = __ldg(p.ep.lam + n + e);
-                      o[e] += (1.f - l) * __ldg(res_row + __ldg(p.ep.i0 + n + e)) + l * __ldg(res_row + __ldg(p.ep.i1 + n + e));
-                    }
-                  }
-                }
-                *reinterpret_cast<float4*>(p.y + r * p.ldy + p.y_col0 + ecol0 + n) = make_float4(o[0], o[1], o[2], o[3]);
-              }
-            }
+            if (res_reg && cb + 32 < N) rv[h][i] = res_piece(i, n + 32);  // same chunk, 32 columns further on
           }
           __syncwarp();
         }
@@ -783,7 +807,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 2);
       if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
     }
-  } else if (p.apack == nullptr) {
+  } else {
+    if (p.apack == nullptr) {
     // ------------------------------------------------------------ producers (16 warps)
     const int q = tid & 7;     // float4 lane inside the 32-feature chunk
     const int rg = tid >> 3;   // row group 0..63
@@ -969,6 +994,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       if (tid == 0) trace_ev(p, 0, ptn, 8);
       if (tid == 0) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the loaders may refill it
       if (tid == 0 && c == n_chunk - 1) mbar_arrive(smem_u32(b_m_empty + m));
+    }
     }
   }
   tc_fence_before();
@@ -1564,6 +1590,23 @@ bool make_row_tmap(CUtensorMap* tm, const float* base, long long rows, int fin, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The conv kernel's setmaxnreg split is balanced for a launch allocation of REGS_LAUNCH registers per thread: a build
+// that ends up with another count would leave the epilogue's setmaxnreg.inc spinning on an empty pool.
+template <int N, int NS, int XS, int RM>
+int check_launch_regs() {
+  static int state = 0;  // per instantiation; racing first calls all compute the same value
+  if (state == 0) {
+    cudaFuncAttributes fa;
+    P2M_CUDA_OK(cudaFuncGetAttributes(&fa, k_cheb_conv_umma<N, NS, XS, RM>));
+    state = (fa.numRegs == REGS_LAUNCH) ? 1 : -1;
+  }
+  if (state < 0) {
+    set_error("k_cheb_conv_umma was compiled with a register count other than the one its setmaxnreg split assumes");
+    return P2M_ERR_CUDA;
+  }
+  return P2M_OK;
+}
+
 template <int N, int NS, int XS, int RM = 0>
 int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
   const DevLevel& g = *a.g;
@@ -1571,6 +1614,7 @@ int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm
   const size_t smem = smem_bytes_args(N, NS, XS, a);
   auto kern = k_cheb_conv_umma<N, NS, XS, RM>;
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  P2M_TRY((check_launch_regs<N, NS, XS, RM>()));
   KParams p;
   p.x = a.x;
   p.in_unpool = a.in_unpool;
@@ -2284,6 +2328,7 @@ int launch_gemm_cfg(KParams p, int n_slices, int sm_count, cudaStream_t s) {
   constexpr int NS = (N == 256) ? 2 : 3;
   const size_t smem = smem_bytes_dims(N, NS, 1, 0, 0, 0, 2);
   auto kern = k_cheb_conv_umma<N, NS, 1, 0>;
+  P2M_TRY((check_launch_regs<N, NS, 1, 0>()));
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.wslice_bytes = (long long)umma_gemm_wpack_bytes(N, p.fin);
   const dim3 grid(std::min(p.n_tiles, sm_count), n_slices);
