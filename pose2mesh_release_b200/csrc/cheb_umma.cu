@@ -713,6 +713,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       // only the first epilogue warp polls the mbarrier, the other three sleep in a hardware barrier until it has seen
       // the accumulator (four polling warps were 12 % of the kernel's executed instructions: a suspended try_wait wakes
       // on every mbarrier event of the CTA, i.e. every ~100 cycles here)
+      bool released = false;
       if (warp == W_EPI0) mbar_wait_relaxed(smem_u32(b_acc_full + as), (it >> 1) & 1, abort_flag, p.status, 7);
       epilogue_barrier();
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 1);
@@ -751,6 +752,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       for (int cb = 0; cb < N; cb += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * N + cb), v);
+        if (cb == N - 32) {  // the whole accumulator has been read: hand the TMEM buffer back before the last slab's stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
+          released = true;
+        }
 #pragma unroll
         for (int h = 0; h < 32 / EC; ++h) {
           // phase 1: lane = row
@@ -802,10 +809,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           __syncwarp();
         }
       }
-      tc_fence_before();
-      __syncwarp();
       if (warp == W_EPI0 && lane == 0) trace_ev(p, 3, etn, 2);
-      if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(b_acc_empty + as));
+      }
     }
   } else {
     if (p.apack == nullptr) {
@@ -932,7 +941,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       const uint32_t slot0 = slot;
       auto emit = [&](const float4& v0, const float4& v1) {
         const uint32_t s = slot;
-        mbar_wait(smem_u32(b_ab_empty + s), spar ^ 1u, abort_flag, p.status, 10);
+        if (NS < 3) mbar_wait(smem_u32(b_ab_empty + s), spar ^ 1u, abort_flag, p.status, 10);
         const uint32_t ablk = ring_a + s * SLOT_BYTES;
 #pragma unroll
         for (int ps = 0; ps < 2; ++ps) {
@@ -976,6 +985,16 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         const float4 x0 = lds_f4(xs_q + (row0 >> xsh) * 128), x1 = lds_f4(xs_q + (row1 >> xsh) * 128);
         const float4 t10 = lds_f4(t1s_q + row0 * 128), t11 = lds_f4(t1s_q + row1 * 128);
         if (tid == 0) trace_ev(p, 0, ptn, 6);
+        {
+          // one wait for the chunk's three slots: the MMA issuer commits them in order, so the last one being free
+          // implies the other two (each mbarrier wait is a ~200-cycle round trip on the critical path of the chunk)
+          uint32_t s2 = slot + 2, p2 = spar;
+          if (s2 >= (uint32_t)NS) {
+            s2 -= (uint32_t)NS;
+            p2 ^= 1u;
+          }
+          mbar_wait(smem_u32(b_ab_empty + s2), p2 ^ 1u, abort_flag, p.status, 10);
+        }
         emit(x0, x1);
         emit(t10, t11);
         emit(cheb_t2(g0, x0),
