@@ -386,9 +386,14 @@ static_assert(W_XLOAD % 4 == 0 && W_EPI0 % 4 == 0 && W_EPI0 - W_XLOAD == 4, "set
 // RM = 1: the residual is the 2:1 channel resampling of a 2N-wide tensor (F.interpolate(linear, align_corners=False)
 // from 2N to N channels is the mean of channel pairs: src = 2j + 0.5), fetched as two 16-byte loads per four outputs
 // instead of the generic 2-tap gather; a separate instantiation so that the other layers keep their register budget.
-template <int N, int NS, int XS, int RM = 0>
+// MODE 1: the production configuration — T1 given, not the plain-GEMM mode — fixed at compile time, so the on-chip first
+// sparse product, the plain path and their per-tile state drop out of the producers (registers for a deeper gather);
+// MODE 0 decides both at run time (plain GEMM, dense GEMM, the split_t1 = 0 ablation).
+template <int N, int NS, int XS, int RM = 0, int MODE = 0>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid_constant__ KParams p) {
   constexpr bool PAIR = (RM == 1);
+  constexpr bool KT1 = (MODE == 1);
+  const bool plain = KT1 ? false : (p.plain != 0);
   constexpr int B_BLOCK_BYTES = N * 128;
   constexpr int SLOT_BYTES = A_BLOCK_BYTES + B_BLOCK_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16(TILE_M, N);
@@ -396,13 +401,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;  // 128B-swizzled blocks need 1024-byte alignment (checked below)
-  const bool t1g = (p.t1 != nullptr);
+  const bool t1g = KT1 ? true : (p.t1 != nullptr);
   float* Xs = reinterpret_cast<float*>(ring + NS * SLOT_BYTES);                 // [XS][max_h2 | 128][32]
-  const size_t xs_stage_floats = (size_t)((t1g || p.plain) ? TILE_M : p.max_h2) * FC;
+  const size_t xs_stage_floats = (size_t)((t1g || plain) ? TILE_M : p.max_h2) * FC;
   float* T1s = Xs + XS * xs_stage_floats;                                       // [1 | XS | 0][max_h1][32]
   const size_t t1_stage_floats = (size_t)p.max_h1 * FC;
   unsigned char* meta_s =
-      reinterpret_cast<unsigned char*>(T1s + (p.plain ? 0 : (t1g ? XS : 1)) * t1_stage_floats);  // [2][meta_stride]
+      reinterpret_cast<unsigned char*>(T1s + (plain ? 0 : (t1g ? XS : 1)) * t1_stage_floats);  // [2][meta_stride]
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta_s + 2 * (size_t)p.meta_stride);
   // barrier map
   uint64_t* b_ab_full = bars;                // [NS]
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
             if (t1g) stage_rows(t1_dst, t1_mesh, TILE_M, h1, 0);  // only the halo rows are left
           } else {
             if (t1g) stage_rows(t1_dst, t1_mesh, 0, h1, 0);
-            stage_rows(x_dst, x_mesh, 0, (p.plain || t1g) ? TILE_M : h2, sh);
+            stage_rows(x_dst, x_mesh, 0, (plain || t1g) ? TILE_M : h2, sh);
             if (lt == 32) mbar_arrive(xbar);
           }
           cp_async_arrive_noinc(xbar);  // this thread's arrival once its copies have landed
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     if (lane == 0) {
       uint32_t ucnt = 0;
       int tn = 0;
-      const int uses = p.plain ? n_chunk : n_use;
+      const int uses = plain ? n_chunk : n_use;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int u = 0; u < uses; ++u, ++ucnt) {
           const int s = ucnt % NS;
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         trace_ev(p, 2, tn, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
-        const int uses = p.plain ? n_chunk : n_use;
+        const int uses = plain ? n_chunk : n_use;
         for (int u = 0; u < uses; ++u, ++ucnt) {
           const int s = ucnt % NS;
           mbar_wait(smem_u32(b_ab_full + s), (ucnt / NS) & 1, abort_flag, p.status, 6);
@@ -864,7 +869,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         const uint32_t mb_a = smem_u32(mb);
         const uint32_t rp_a = mb_a + hdr->off_rp, ord1_a = mb_a + hdr->off_ord1, ord2_a = mb_a + hdr->off_ord2;
         ent_a = mb_a + hdr->off_ent;
-        const int h1 = (t1g || p.plain) ? 0 : hdr->h1;  // the trimmed metadata has no T1 row order
+        const int h1 = (t1g || plain) ? 0 : hdr->h1;  // the trimmed metadata has no T1 row order
 #pragma unroll
         for (int t = 0; t < T1_ROWS; ++t) {
           const int j = rg + 64 * t;
@@ -879,7 +884,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         row1 = lds_u16(ord2_a + 2 * (64 + rg));
         r0e = lds_u16(rp_a + 2 * row0) | (lds_u16(rp_a + 2 * row0 + 2) << 16);
         r1e = lds_u16(rp_a + 2 * row1) | (lds_u16(rp_a + 2 * row1 + 2) << 16);
-        if (p.plain) {  // plain GEMM: the thread's rows are the consecutive slots rg and 64 + rg
+        if (plain) {  // plain GEMM: the thread's rows are the consecutive slots rg and 64 + rg
           row0 = rg;
           row1 = 64 + rg;
         }
@@ -893,7 +898,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       }
       const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
       const uint32_t t1s_q = t1s_a + (t1g ? (uint32_t)(xs * t1_stage_floats * 4) : 0u) + q * 16;
-      if (p.plain) {
+      if (plain) {
         // plain GEMM: the staged rows ARE the A operand (scaled into fp16 range if a_scale is given)
         const uint32_t s = slot;
         mbar_wait(smem_u32(b_ab_empty + s), spar ^ 1u, abort_flag, p.status, 10);
@@ -1611,12 +1616,12 @@ bool make_row_tmap(CUtensorMap* tm, const float* base, long long rows, int fin, 
 
 // The conv kernel's setmaxnreg split is balanced for a launch allocation of REGS_LAUNCH registers per thread: a build
 // that ends up with another count would leave the epilogue's setmaxnreg.inc spinning on an empty pool.
-template <int N, int NS, int XS, int RM>
+template <int N, int NS, int XS, int RM, int MODE>
 int check_launch_regs() {
   static int state = 0;  // per instantiation; racing first calls all compute the same value
   if (state == 0) {
     cudaFuncAttributes fa;
-    P2M_CUDA_OK(cudaFuncGetAttributes(&fa, k_cheb_conv_umma<N, NS, XS, RM>));
+    P2M_CUDA_OK(cudaFuncGetAttributes(&fa, k_cheb_conv_umma<N, NS, XS, RM, MODE>));
     state = (fa.numRegs == REGS_LAUNCH) ? 1 : -1;
   }
   if (state < 0) {
@@ -1626,14 +1631,16 @@ int check_launch_regs() {
   return P2M_OK;
 }
 
-template <int N, int NS, int XS, int RM = 0>
+template <int N, int NS, int XS, int RM = 0, int MODE = 0>
 int launch_cfg(const UmmaConvArgs& a, int* status, const float* zero_row, int sm_count, cudaStream_t s) {
+  if (MODE == 0 && a.t1 != nullptr && !a.plain)  // the production configuration has its own instantiation
+    return launch_cfg<N, NS, XS, RM, 1>(a, status, zero_row, sm_count, s);
   const DevLevel& g = *a.g;
   const int mode = a.plain ? 2 : (a.t1 != nullptr ? 1 : 0);
   const size_t smem = smem_bytes_args(N, NS, XS, a);
-  auto kern = k_cheb_conv_umma<N, NS, XS, RM>;
+  auto kern = k_cheb_conv_umma<N, NS, XS, RM, MODE>;
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  P2M_TRY((check_launch_regs<N, NS, XS, RM>()));
+  P2M_TRY((check_launch_regs<N, NS, XS, RM, MODE>()));
   KParams p;
   p.x = a.x;
   p.in_unpool = a.in_unpool;
@@ -2347,7 +2354,7 @@ int launch_gemm_cfg(KParams p, int n_slices, int sm_count, cudaStream_t s) {
   constexpr int NS = (N == 256) ? 2 : 3;
   const size_t smem = smem_bytes_dims(N, NS, 1, 0, 0, 0, 2);
   auto kern = k_cheb_conv_umma<N, NS, 1, 0>;
-  P2M_TRY((check_launch_regs<N, NS, 1, 0>()));
+  P2M_TRY((check_launch_regs<N, NS, 1, 0, 0>()));
   P2M_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.wslice_bytes = (long long)umma_gemm_wpack_bytes(N, p.fin);
   const dim3 grid(std::min(p.n_tiles, sm_count), n_slices);

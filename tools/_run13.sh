@@ -1,9 +1,4 @@
-set -x
 mkdir -p gpurun_out
-timeout 180 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1 || { echo SMOKE FAILED; tail -5 gpurun_out/smoke.log; exit 1; }
-tail -1 gpurun_out/smoke.log
-( time timeout 600 python -m pytest tests -m gpu -q -x ) > gpurun_out/r2_pytest_gpu.log 2>&1
-grep -n '^E  \|^FAILED\|passed\|failed' gpurun_out/r2_pytest_gpu.log | head -40
 timeout 300 python bench.py --steps 5 --warmup 3 --cpu-sample 0 --train-steps 3 > gpurun_out/r2_bench_c.json 2> gpurun_out/r2_bench_c.err
 python - <<'PY'
 import json
