@@ -393,6 +393,10 @@ template <int N, int NS, int XS, int RM = 0, int MODE = 0>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid_constant__ KParams p) {
   constexpr bool PAIR = (RM == 1);
   constexpr bool KT1 = (MODE == 1);
+  // X of the own rows straight from global memory (production mode, deep ring): the only reader of an own X row is the
+  // producer thread that emits it, so staging it costs a shared-memory write plus a read back (8 % of the kernel's
+  // shared-memory traffic, and more than half of the loaders' copies on index-list tiles) for nothing
+  constexpr bool XDIRECT = KT1 && NS >= 3;
   const bool plain = KT1 ? false : (p.plain != 0);
   constexpr int B_BLOCK_BYTES = N * 128;
   constexpr int SLOT_BYTES = A_BLOCK_BYTES + B_BLOCK_BYTES;
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       const int lq = lt & 7, lrg = lt >> 3;
       const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       if (lt == 32 && p.tma) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_x)) : "memory");
+        if (!XDIRECT) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_x)) : "memory");
         if (t1g) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tm_t1)) : "memory");
       }
       auto fetch_meta = [&](int itf) {  // thread 0: blob of this CTA's tile number itf into buffer itf & 1
@@ -549,14 +553,15 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           if (p.tma) {
             if (lt == 32) {
               const int own0 = tile2 * TILE_M;  // V is a multiple of 128: tiles never straddle meshes
-              mbar_arrive_expect_tx(xbar, (p.in_unpool ? TILE_M / 2 : TILE_M) * 128 + (t1g ? TILE_M * 128 : 0));
-              tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
+              mbar_arrive_expect_tx(xbar, (XDIRECT ? 0 : (p.in_unpool ? TILE_M / 2 : TILE_M) * 128) + (t1g ? TILE_M * 128 : 0));
+              if (!XDIRECT)
+                tma_load_2d(smem_u32(Xs + xs2 * xs_stage_floats), &p.tm_x, c2 * FC, p.in_unpool ? own0 >> 1 : own0, xbar);
               if (t1g) tma_load_2d(smem_u32(T1s + xs2 * t1_stage_floats), &p.tm_t1, c2 * FC, own0, xbar);
             }
             if (t1g) stage_rows(t1_dst, t1_mesh, TILE_M, h1, 0);  // only the halo rows are left
           } else {
             if (t1g) stage_rows(t1_dst, t1_mesh, 0, h1, 0);
-            stage_rows(x_dst, x_mesh, 0, (plain || t1g) ? TILE_M : h2, sh);
+            if (!XDIRECT) stage_rows(x_dst, x_mesh, 0, (plain || t1g) ? TILE_M : h2, sh);
             if (lt == 32) mbar_arrive(xbar);
           }
           cp_async_arrive_noinc(xbar);  // this thread's arrival once its copies have landed
@@ -850,6 +855,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     };
 
     const int xsh = (p.tma && p.in_unpool) ? 1 : 0;  // TMA-staged unpooled input: staged row = tile row >> 1
+    const float* xp0 = nullptr;  // XDIRECT: this thread's two own X rows (nullptr: empty slot), at its 16-byte column
+    const float* xp1 = nullptr;
     int it = 0, c = -1;
     for (int g = 0; g < n_stage; ++g) {
       if (++c == n_chunk) {
@@ -858,6 +865,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
       }
       const int m = it & 1;
       const int xs = g % XS;
+      float4 xd0 = make_float4(0.f, 0.f, 0.f, 0.f), xd1 = xd0;
+      if (XDIRECT && c != 0) {  // in flight while the stage wait and the gather run (first chunk: below, after the tile setup)
+        if (xp0) xd0 = __ldg(reinterpret_cast<const float4*>(xp0 + c * FC));
+        if (xp1) xd1 = __ldg(reinterpret_cast<const float4*>(xp1 + c * FC));
+      }
       if (tid == 0) trace_ev(p, 0, ptn, 1);
       mbar_wait(smem_u32(b_x_full + xs), (g / XS) & 1, abort_flag, p.status, 9);
       if (tid == 0) trace_ev(p, 0, ptn, 2);
@@ -894,6 +906,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           const uint32_t a_hi = sw128_off(i, q >> 1) + (q & 1) * 8, a_lo = sw128_off(i, 4 + (q >> 1)) + (q & 1) * 8;
           so_f[ps] = odd ? a_lo : a_hi;
           so_s[ps] = odd ? a_hi : a_lo;
+        }
+        if (XDIRECT) {
+          const int* halo = reinterpret_cast<const int*>(mb + hdr->off_halo);  // slots 0..127 = the tile's own rows
+          const int v0 = halo[row0], v1 = halo[row1];
+          const int sh = p.in_unpool ? 1 : 0;
+          const long long mesh_row0 = (long long)((blockIdx.x + (unsigned)it * gridDim.x) / (unsigned)p.P) * p.V;
+          const float* xm = p.x + (mesh_row0 >> sh) * p.fin + q * 4;
+          xp0 = (v0 >= 0) ? xm + (size_t)((uint32_t)v0 >> sh) * (uint32_t)p.fin : nullptr;
+          xp1 = (v1 >= 0) ? xm + (size_t)((uint32_t)v1 >> sh) * (uint32_t)p.fin : nullptr;
+          if (xp0) xd0 = __ldg(reinterpret_cast<const float4*>(xp0));
+          if (xp1) xd1 = __ldg(reinterpret_cast<const float4*>(xp1));
         }
       }
       const uint32_t xs_q = smem_u32(Xs + xs * xs_stage_floats) + q * 16;
@@ -987,7 +1010,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         // the gather then overlaps the previous chunk's tail instead of this chunk's own stores)
         const float4 g0 = gather_row4(ent_a, r0e & 0xFFFFu, r0e >> 16, t1s_q);
         const float4 g1 = gather_row4(ent_a, r1e & 0xFFFFu, r1e >> 16, t1s_q);
-        const float4 x0 = lds_f4(xs_q + (row0 >> xsh) * 128), x1 = lds_f4(xs_q + (row1 >> xsh) * 128);
+        const float4 x0 = XDIRECT ? xd0 : lds_f4(xs_q + (row0 >> xsh) * 128);
+        const float4 x1 = XDIRECT ? xd1 : lds_f4(xs_q + (row1 >> xsh) * 128);
         const float4 t10 = lds_f4(t1s_q + row0 * 128), t11 = lds_f4(t1s_q + row1 * 128);
         if (tid == 0) trace_ev(p, 0, ptn, 6);
         {
