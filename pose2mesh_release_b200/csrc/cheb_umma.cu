@@ -6,14 +6,16 @@
 //                    gathers out of shared memory.
 // k_cheb_conv_umma — one persistent CTA per SM; a tile is 128 consecutive vertices of one mesh (a compact patch: the
 //                    reference's binary-tree vertex order makes rows [128p,128p+128) the descendants of one coarse node).
-//   * 16 producer warps build the A operand on chip, 32 features at a time.  They stage the tile's own X and T1
-//     rows (one 2-D TMA box each) and the T1 rows of the 1-hop halo (16-byte cp.async, completion through
-//     cp.async.mbarrier.arrive.noinc) one chunk ahead, run the second sparse product from shared memory with a
-//     tile-local CSR, split every fp32 value into an fp16 (hi, lo) pair and write it straight into the
-//     128B-swizzled K-major UMMA layout.  T2 is never materialised in HBM.  (Without a T1 buffer — p.t1 == nullptr —
-//     the same kernel stages the 2-hop halo of X and runs both sparse products on chip: the fully fused variant.)
-//   * 1 thread prefetches the next tile's metadata blob, 1 thread streams the pre-packed fp16 (hi|lo) weight
-//     blocks, both with cp.async.bulk (TMA engine, mbarrier complete_tx).
+//   * 16 producer warps build the A operand on chip, 32 features at a time: they run the second sparse product from
+//     shared memory with a tile-local CSR (the T1 rows of the tile and its 1-hop halo, staged one chunk ahead), read
+//     their own X rows straight from global memory, split every fp32 value into an fp16 (hi, lo) pair and write it
+//     into the 128B-swizzled K-major UMMA layout.  T2 is never materialised in HBM.  (Without a T1 buffer —
+//     p.t1 == nullptr, the split_t1 = 0 ablation — the same kernel stages the 2-hop halo of X and runs both sparse
+//     products on chip: the fully fused variant.)
+//   * 2 loader warps stage what the producers gather from: the tile's own T1 rows as one 2-D TMA box where the tile
+//     is a run of consecutive rows, every other row (halo, index-list tiles) by 16-byte cp.async with completion
+//     through cp.async.mbarrier.arrive.noinc; thread 0 also prefetches the next tile's metadata blob.  1 thread
+//     streams the pre-packed fp16 (hi|lo) weight blocks (cp.async.bulk, mbarrier complete_tx).
 //   * 1 thread issues tcgen05.mma (kind::f16, M=128, N=Fout, K=16) into a double-buffered TMEM accumulator:
 //     per 16 features three MMAs — hi*Whi + lo*Whi + hi*Wlo — an error-compensated product with ~2^-21
 //     relative error, which is what keeps the 1e-4 fp32 parity bar (plain TF32/FP16 does not, SURVEY.md §7
@@ -45,8 +47,6 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int FC = 32;                         // features per chunk (= 128 B of fp32 per row)
 constexpr int A_BLOCK_BYTES = TILE_M * 128;    // one K-block of A: 128 rows x (32 hi | 32 lo) fp16
-constexpr int NUM_WORKERS = 256;               // 8 producer / epilogue warps
-constexpr int NUM_THREADS = NUM_WORKERS + 64;  // + warp 8 (weight loader) + warp 9 (MMA issuer, TMEM owner)
 constexpr float W_SCALE = 64.f;
 constexpr float W_INV_SCALE = 1.f / 64.f;
 
@@ -368,10 +368,10 @@ __device__ __forceinline__ void trace_ev(const KParams& p, int role, int& n, int
 __device__ __forceinline__ void trace_ev(const KParams&, int, int&, int) {}
 #endif
 
-// Warp roles (24 warps, one persistent CTA per SM):
+// Warp roles (24 warps = 6 warpgroups, one persistent CTA per SM):
 //   0..15  producers: SpMM out of shared memory + fp16 (hi,lo) split + swizzled A-block stores
-//   16     thread 0 fetches the next tile's metadata (cp.async.bulk); warp 17 is idle (the rows are staged by the
-//          producers since the first sparse product moved out of this kernel)
+//   16,17  loaders: stage the T1 (and, outside the production mode, X) rows of the next chunk; thread 0 also fetches
+//          the next tile's metadata (cp.async.bulk), thread 32 issues the TMA boxes
 //   18     weight-block loader (one thread, cp.async.bulk)
 //   19     MMA issuer (one thread) and TMEM owner
 //   20..23 epilogue: TMEM -> registers -> fused epilogue -> HBM, overlapped with the next tile's main loop
