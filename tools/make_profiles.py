@@ -69,7 +69,9 @@ def ncu_full():
         v, u = float(d[k].replace(",", "")), units[hdr.index(k)]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
 
-    layer = per[:3]
+    # capture order (-s 77 -c 6): conv + plain GEMM of the second V=6144 layer, then T1 / conv / plain GEMM of the first
+    # V=12288 128->128 layer, then the T1 pass of the next layer
+    layer = per[2:5]
     traffic = {"source": "profiles/r2_umma_ncu_summary.txt (ncu --set full --clock-control none, first V=12288 128->128 layer of the "
                          "eval forward at B=256, shipped configuration: padding-vertex elision + duplicate elimination)",
                "batch": 256, "V": 12288, "fin": 128, "fout": 128, "kernels": {}, "layer_dram_bytes": 0.0}
@@ -81,12 +83,19 @@ def ncu_full():
         traffic["layer_dram_bytes"] += rd + wr
     json.dump(traffic, open(os.path.join(PR, "r2_ncu_traffic.json"), "w"), indent=1)
     # shared-memory wavefronts of the conv kernel by opcode (source page)
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:conv_umma"],
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    # the source page lists every captured kernel (twice): take the section whose executed-instruction total is the
+    # largest, i.e. the V=12288 conv kernel on the connected-row tiles (kernel 3 above)
+    def section_total(k):
+        h, end = rows[his[k]], (his[k + 1] if k + 1 < len(his) else len(rows))
+        c = h.index("Instructions Executed")
+        return sum(int(r[c] or 0) for r in rows[his[k] + 1:end] if len(r) == len(h) and r[0].startswith("0x"))
     if his:
-        hi, end = his[0], (his[1] if len(his) > 1 else len(rows))
+        best = max(range(len(his)), key=section_total)
+        hi, end = his[best], (his[best + 1] if best + 1 < len(his) else len(rows))
         h = rows[hi]
         idx = {c: i for i, c in enumerate(h)}
         seen, u = set(), []
