@@ -28,5 +28,5 @@ for r in rows: print("| " + " | ".join(r) + " |")
 if n1:
     r = n1["roofline"]
     print(f"\nDominant layer (V=12288, 128→128, B=256): {r['ms_per_launch']:.2f} ms → {r['achieved']:.0f} GB/s of algorithmic bytes = "
-          f"**{r['frac']:.3f} of the measured HBM peak** ({r['peak']:.0f} GB/s); DRAM traffic of the layer {r['traffic'] / 1e9:.2f} GB "
+          f"**{r['frac']:.3f} of the measured HBM peak** ({r['peak']:.0f} GB/s); DRAM traffic of the layer {json.load(open(os.path.join(P, 'r2_ncu_traffic.json')))['layer_dram_bytes'] / 1e9:.2f} GB "
           f"vs {r['algorithmic_bytes'] / 1e9:.2f} GB algorithmic.")
