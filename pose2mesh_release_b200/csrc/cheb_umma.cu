@@ -835,7 +835,6 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
     const uint32_t ring_a = smem_u32(ring);
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_stage = my_tiles * n_chunk;  // flat sequence of (tile, chunk) stages of this CTA
-    uint32_t ucnt = 0;
 
     constexpr int T1_ROWS = 4;  // max_h1 <= 256 rows over 64 row groups (checked on the host)
     uint32_t t1_row[T1_ROWS], t1_e[T1_ROWS];
@@ -941,7 +940,6 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
         fence_async_proxy();
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
-        ++ucnt;
         next_slot();
         producer_barrier();
         if (tid == 0) mbar_arrive(smem_u32(b_x_empty + xs));  // stage free: the loaders may refill it
@@ -990,7 +988,6 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) k_cheb_conv_umma(const __grid
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(smem_u32(b_ab_full + s));
         }
-        ++ucnt;
         next_slot();
       };
       if (NS < 3) {

@@ -34,7 +34,7 @@ for role in range(4):
 ev_all.sort()
 t0 = ev_all[0][0]
 print(f"V={V} {fin}->{fout} B={B}: first 260 events of CTA 0 (cycles since start)")
-pn = {20: "issue_stage begin", 21: "copies issued", 22: "noinc arrive done", 1: "wait_x", 2: "x_ready", 4: "T1 gathered", 5: "T1 barrier passed", 6: "T2 gathered", 7: "blocks emitted", 8: "end barrier"}
+pn = {1: "wait_x", 2: "x_ready", 4: "T1 gathered", 5: "T1 barrier passed", 6: "T2 gathered", 7: "blocks emitted", 8: "end barrier"}
 for c, role, ev in ev_all[:260]:
     if role == 0:
         label = pn.get(ev, str(ev))
