@@ -27,6 +27,30 @@ def test_library_loads_and_exports_header_symbols():
     assert b"sm_100a" in lib.p2m_version()
 
 
+def test_conv_kernel_register_split_is_balanced_in_the_build():
+    """k_cheb_conv_umma redistributes registers between its warpgroups with setmaxnreg (csrc/cheb_umma.cu: REGS_*): the
+    epilogue's setmaxnreg.inc draws on exactly what the utility warpgroup's setmaxnreg.dec released, which only works
+    out if every instantiation is LAUNCHED with 80 registers per thread.  The host refuses to launch otherwise
+    (check_launch_regs); this catches such a build here, without a GPU."""
+    import shutil
+    import subprocess
+
+    from pose2mesh_release_b200 import build
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = build.build()
+    out = subprocess.run([cuobjdump, "-res-usage", lib], capture_output=True, text=True).stdout
+    regs = re.findall(r"Function [^\n]*k_cheb_conv_umma[^\n]*\n[^\n]*REG:(\d+)", out)
+    assert len(regs) >= 10, f"conv kernel instantiations not found in {lib}"
+    assert set(regs) == {"80"}, f"launch register counts of k_cheb_conv_umma: {sorted(set(regs))}"
+    src = open(os.path.join(ROOT, "pose2mesh_release_b200", "csrc", "cheb_umma.cu")).read()
+    m = re.search(r"REGS_LAUNCH = (\d+), REGS_UTIL = (\d+), REGS_EPI = (\d+)", src)
+    launch, util, epi = (int(v) for v in m.groups())
+    assert launch == 80 and epi - launch <= launch - util and util % 8 == 0 and epi % 8 == 0
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "pose2mesh_release_b200")
     for fn in os.listdir(pkg):
